@@ -1,0 +1,82 @@
+"""ctypes binding of libgptq_b200.so (the C ABI declared in include/gptq_b200.h).
+
+There is NO fallback: if the shared library is missing or a symbol is absent, importing this
+module raises.  The library has no torch dependency; torch only supplies device pointers and
+the current stream.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), 'libgptq_b200.so')
+
+ABI_VERSION = 1
+
+c_void_p, c_int, c_int64, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
+
+
+class QWeight(ctypes.Structure):
+    """struct gptq_qweight (include/gptq_b200.h)."""
+    _fields_ = [
+        ('qweight', c_void_p),
+        ('scales', c_void_p),
+        ('qzeros', c_void_p),
+        ('g_idx', c_void_p),
+        ('K', c_int),
+        ('N', c_int),
+        ('G', c_int),
+        ('bits', c_int),
+        ('groupsize', c_int),
+    ]
+
+
+_QW = ctypes.POINTER(QWeight)
+
+# name -> (restype, argtypes); must list every symbol include/gptq_b200.h declares
+SIGNATURES = {
+    'gptq_abi_version': (c_int, []),
+    'gptq_strerror': (ctypes.c_char_p, [c_int]),
+    'gptq_qlinear_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'gptq_qlinear_fwd': (c_int, [c_void_p, c_int64, _QW, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    'gptq_fused_mlp_fwd': (c_int, [c_void_p, c_int64, _QW, _QW, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    'gptq_qlinear_transpose_fwd': (c_int, [c_void_p, c_int64, _QW, c_void_p, c_int64, c_int, c_void_p]),
+    'gptq_rope_inplace': (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    'gptq_rmsnorm_fwd': (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p]),
+    'gptq_pack_qweight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'gptq_pack_qzeros': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'gptq_unpack_qweight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'gptq_unpack_qzeros': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'gptq_dequant': (c_int, [_QW, c_void_p, c_int64, c_void_p]),
+}
+
+# gptq_status (include/gptq_b200.h)
+OK, ERR_BITS, ERR_SHAPE, ERR_NULL, ERR_ALIGN, ERR_WORKSPACE, ERR_CUDA, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f'{LIB_PATH} not found: build it with `make -C gptq-for-llama_b200/csrc` (or __graft_entry__.build()). '
+                          'There is no CPU / PyTorch fallback for the quantized-linear path.')
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing -> fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.gptq_abi_version() != ABI_VERSION:
+        raise ImportError(f'libgptq_b200.so ABI {lib.gptq_abi_version()} != binding ABI {ABI_VERSION}: rebuild')
+    return lib
+
+
+lib = _load()
+
+
+def check(status: int) -> None:
+    """Map a gptq_status to the exception the reference raises at the same place."""
+    if status == OK:
+        return
+    msg = lib.gptq_strerror(status).decode()
+    if status == ERR_BITS:
+        raise NotImplementedError(msg)  # quant/quant_linear.py:308-309
+    if status in (ERR_SHAPE, ERR_ALIGN, ERR_NULL):
+        raise ValueError(msg)
+    raise RuntimeError(msg)  # incl. norm width > 64 KB (quant/triton_norm.py:59-60)

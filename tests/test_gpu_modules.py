@@ -1,0 +1,156 @@
+"""GPU: the reference-facing modules end to end -- QuantLinear / QuantLlamaMLP / QuantLlamaAttention /
+TritonLlamaRMSNorm inside a tiny HF LLaMA, i.e. what llama_inference.load_quant builds -- and
+size-independent properties at BASELINE.json's full layer sizes."""
+import pytest
+import torch
+
+from oracle import gptq_oracle as O
+from gpu_util import assert_rel_close, cuda
+
+pytestmark = pytest.mark.gpu
+
+
+def _fill(ql, bits, seed, act=False):
+    qw, s, qz, g, b = O.random_packed(ql.infeatures, ql.outfeatures, bits, ql.groupsize, act_order=act, seed=seed, bias=ql.bias is not None)
+    ql.qweight, ql.scales, ql.qzeros, ql.g_idx = qw, s, qz, g
+    if b is not None:
+        ql.bias = b
+
+
+@pytest.mark.parametrize('bits,act', [(4, False), (4, True), (3, True), (8, False), (2, False)])
+def test_quantlinear_module_forward_and_backward(bits, act):
+    import quant
+    ql = quant.QuantLinear(bits, 64, 256, 128, True)
+    _fill(ql, bits, seed=bits, act=act)
+    x = torch.randn(2, 3, 256, generator=torch.Generator().manual_seed(0)).half()
+    ref = O.qlinear_fwd(x, ql.qweight, ql.scales, ql.qzeros, ql.g_idx, bits, ql.bias)
+    ql = ql.cuda()
+    assert ql.groupsize_hint() == (0 if act else 64)
+    xd = x.cuda().requires_grad_(True)
+    out = ql(xd)
+    assert out.shape == (2, 3, 128) and out.dtype == torch.float16
+    assert_rel_close(out, ref, what='module fwd')
+    go = torch.randn(2, 3, 128, generator=torch.Generator().manual_seed(1)).half()
+    out.backward(go.cuda())
+    gref = O.qlinear_transpose_fwd(go, *(t.cpu() for t in (ql.qweight, ql.scales, ql.qzeros, ql.g_idx)), bits)
+    assert_rel_close(xd.grad, gref, what='module bwd')
+
+
+def _tiny_quant_llama(bits=4, gs=32, act=False):
+    import quant
+    import utils
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=2, num_attention_heads=4, num_key_value_heads=4, vocab_size=256,
+                      max_position_embeddings=128)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).half().eval()
+    layers = utils.find_layers(model)
+    layers.pop('lm_head')
+    quant.make_quant_linear(model, layers, bits, gs)
+    seed = 0
+    for name, m in model.named_modules():
+        if isinstance(m, quant.QuantLinear):
+            seed += 1
+            # q/k/v of one block share their input, hence their act-order
+            _fill(m, bits, seed, act=False)
+            if act:
+                blk = name.split('.')[2]
+                m.g_idx = O.make_g_idx(m.infeatures, gs, True, torch.Generator().manual_seed(int(blk) + m.infeatures))
+    return model
+
+
+def _ref_forward(model, ids):
+    """fp32 reference forward of the (not yet fused) quantized model using the CPU oracle for every op."""
+    import quant
+    cfg = model.config
+    h = model.model.embed_tokens(ids).half()
+    bsz, seq = ids.shape
+    pos = torch.arange(seq)[None, :].expand(bsz, -1)
+    nh, hd = cfg.num_attention_heads, cfg.hidden_size // cfg.num_attention_heads
+
+    def lin(m, x):
+        return O.qlinear_fwd(x, m.qweight, m.scales, m.qzeros, m.g_idx, m.bits, m.bias)
+
+    for layer in model.model.layers:
+        a = layer.self_attn
+        x = O.rmsnorm_fwd(h, layer.input_layernorm.weight.data, layer.input_layernorm.variance_epsilon)
+        qkv = torch.stack([lin(a.q_proj, x), lin(a.k_proj, x), lin(a.v_proj, x)], dim=2).view(bsz, seq, 3, nh, hd)
+        O.rope_inplace(qkv[:, :, :2], pos)
+        q, k, v = (qkv[:, :, i].transpose(1, 2).float() for i in range(3))
+        att = torch.nn.functional.scaled_dot_product_attention(q, k, v, is_causal=True).half()
+        h = h + lin(a.o_proj, att.transpose(1, 2).reshape(bsz, seq, -1))
+        x = O.rmsnorm_fwd(h, layer.post_attention_layernorm.weight.data, layer.post_attention_layernorm.variance_epsilon)
+        m = layer.mlp
+        inter = O.fused_mlp_fwd(x, (m.gate_proj.qweight, m.gate_proj.scales, m.gate_proj.qzeros, m.gate_proj.g_idx),
+                                (m.up_proj.qweight, m.up_proj.scales, m.up_proj.qzeros, m.up_proj.g_idx), m.gate_proj.bits)
+        h = h + lin(m.down_proj, inter)
+    h = O.rmsnorm_fwd(h, model.model.norm.weight.data, model.model.norm.variance_epsilon)
+    return (h.float() @ model.lm_head.weight.data.float().t())
+
+
+@pytest.mark.parametrize('act', [False, True])
+def test_load_quant_pipeline_on_tiny_llama(act):
+    """make_quant_linear -> (load) -> make_quant_attn / make_quant_norm / make_fused_mlp -> .to(DEV) -> forward,
+    prefill then one cached decode step, against the oracle-composed reference."""
+    import quant
+    model = _tiny_quant_llama(act=act)
+    ids = torch.randint(0, 256, (1, 9), generator=torch.Generator().manual_seed(0))
+    ref_logits = _ref_forward(model, ids)
+    quant.make_quant_attn(model)
+    quant.make_quant_norm(model)
+    quant.make_fused_mlp(model)
+    model = model.cuda()
+    assert quant.autotune_warmup_linear(model) > 0 and quant.autotune_warmup_fused(model) == 2
+    with torch.no_grad():
+        out = model(ids[:, :8].cuda(), use_cache=True)
+        assert_rel_close(out.logits[0], ref_logits[0, :8], rel=2e-2, what='prefill logits')
+        step = model(ids[:, 8:9].cuda(), past_key_values=out.past_key_values, use_cache=True)
+        assert_rel_close(step.logits[0, 0], ref_logits[0, 8], rel=2e-2, what='decode logits')
+
+
+# ----------------------------------------------------------------------------- full BASELINE sizes: size-independent properties
+FULL = [(4096, 4096), (4096, 12288), (11008, 4096)]
+
+
+@pytest.mark.parametrize('K,N', FULL)
+def test_full_size_matches_dequant_matmul(K, N):
+    """LLaMA-7B layer sizes, M=1: CUDA matvec == fp32 matmul over the device-dequantised weight
+    (the dequant kernel itself is pinned bit-exactly to the oracle above)."""
+    from gptq_b200 import ops
+    qw, s, qz, g, _ = cuda(*O.random_packed(K, N, 4, 128, seed=K + N))
+    x = torch.randn(1, K, generator=torch.Generator().manual_seed(0)).half().cuda()
+    W = ops.dequant(qw, s, qz, g, 4, 128)
+    ref = (x.float() @ W.float()).half()
+    out = ops.matmul248(x, qw, s, qz, g, 4, 15, groupsize=128)
+    assert_rel_close(out, ref, what=f'full {K}x{N}')
+    # exact homogeneity: scaling x by a power of two scales every product exactly
+    out2 = ops.matmul248(x * 2, qw, s, qz, g, 4, 15, groupsize=128)
+    assert torch.equal(out2, out * 2)
+    # determinism
+    assert torch.equal(ops.matmul248(x, qw, s, qz, g, 4, 15, groupsize=128), out)
+
+
+def test_full_size_fused_mlp_matches_composition():
+    from gptq_b200 import ops
+    K, N = 4096, 11008
+    gate = cuda(*O.random_packed(K, N, 4, 128, seed=1)[:4])
+    up = cuda(*O.random_packed(K, N, 4, 128, seed=2)[:4])
+    x = torch.randn(1, K, generator=torch.Generator().manual_seed(0)).half().cuda()
+    a1 = x.float() @ ops.dequant(*gate, 4, 128).float()
+    a2 = x.float() @ ops.dequant(*up, 4, 128).float()
+    ref = (a1 * torch.sigmoid(a1) * a2).half()
+    out = ops.fused_mlp(x, gate, up, 4, 128)
+    assert_rel_close(out, ref, rel=2e-3, what='full fused mlp')
+
+
+def test_column_slices_are_independent():
+    """Sharding property used by tensor parallelism: slicing the packed tensors along N (multiples of 32)
+    gives exactly the corresponding slice of the output."""
+    from gptq_b200 import ops
+    K, N = 1024, 512
+    qw, s, qz, g, _ = cuda(*O.random_packed(K, N, 4, 128, seed=9))
+    x = torch.randn(2, K, generator=torch.Generator().manual_seed(0)).half().cuda()
+    full = ops.matmul248(x, qw, s, qz, g, 4, 15)
+    for n0, n1 in ((0, 128), (128, 512), (256, 288)):
+        part = ops.matmul248(x, qw[:, n0:n1].contiguous(), s[:, n0:n1].contiguous(), qz[:, n0 // 8:n1 // 8].contiguous(), g, 4, 15)
+        assert_rel_close(part, full[:, n0:n1], what=f'cols {n0}:{n1}')
