@@ -48,8 +48,23 @@ const char* gptq_strerror(int status) {
 }
 
 size_t gptq_qlinear_workspace_bytes(int M, int K, int N, int bits) {
-    (void)M; (void)K; (void)N; (void)bits;
-    return 0;
+    if (bits != 4 || M <= 0 || K <= 0 || N <= 0) return 0;
+    return skinny_workspace_bytes(M, K, N, false);
+}
+
+size_t gptq_fused_mlp_workspace_bytes(int M, int K, int N, int bits) {
+    if (bits != 4 || M <= 0 || K <= 0 || N <= 0) return 0;
+    return skinny_workspace_bytes(M, K, N, true);
+}
+
+static int run_qlinear(const QLinearArgs& a) {
+    if (skinny_supported(a)) {
+        const size_t need = skinny_workspace_bytes(a.M, a.w.K, a.w.N, a.dual);
+        if (a.workspace == nullptr || a.ws_bytes < need) return GPTQ_ERR_WORKSPACE;
+        if ((reinterpret_cast<uintptr_t>(a.workspace) & 255) != 0) return GPTQ_ERR_ALIGN;
+        return cuda_status(launch_qlinear_skinny(a, false));
+    }
+    return cuda_status(launch_qlinear_generic(a));
 }
 
 int gptq_qlinear_fwd(const void* x, int64_t ldx, const gptq_qweight* w, const void* bias, void* out, int64_t ldo, int M, void* workspace, size_t ws_bytes,
@@ -62,7 +77,7 @@ int gptq_qlinear_fwd(const void* x, int64_t ldx, const gptq_qweight* w, const vo
     QLinearArgs a{};
     a.x = x; a.ldx = ldx; a.w = *w; a.dual = false; a.bias = bias; a.out = out; a.ldo = ldo; a.M = M;
     a.workspace = workspace; a.ws_bytes = ws_bytes; a.stream = static_cast<cudaStream_t>(stream);
-    return cuda_status(launch_qlinear_generic(a));
+    return run_qlinear(a);
 }
 
 int gptq_fused_mlp_fwd(const void* x, int64_t ldx, const gptq_qweight* gate, const gptq_qweight* up, void* out, int64_t ldo, int M, void* workspace,
@@ -79,7 +94,7 @@ int gptq_fused_mlp_fwd(const void* x, int64_t ldx, const gptq_qweight* gate, con
     QLinearArgs a{};
     a.x = x; a.ldx = ldx; a.w = *gate; a.w2 = *up; a.dual = true; a.bias = nullptr; a.out = out; a.ldo = ldo; a.M = M;
     a.workspace = workspace; a.ws_bytes = ws_bytes; a.stream = static_cast<cudaStream_t>(stream);
-    return cuda_status(launch_qlinear_generic(a));
+    return run_qlinear(a);
 }
 
 int gptq_qlinear_transpose_fwd(const void* g, int64_t ldg, const gptq_qweight* w, void* out, int64_t ldo, int M, gptq_stream_t stream) {

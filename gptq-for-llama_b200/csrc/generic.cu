@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(32 * kGenWarps) qlinear_generic_kernel(const _
                     o = __float2half_rn(swiglu(a, b));
                 } else {
                     o = __float2half_rn(a);
-                    if (bias != nullptr) o = __hadd(o, __ldg(bias + n));  // fp16 add after the store rounding (quant_linear.py:376)
+                    if (bias != nullptr) o = __hadd(o, bias[n]);  // fp16 add after the store rounding (quant_linear.py:376)
                 }
                 out[(size_t)(m0 + m) * ldo + n] = o;
             }

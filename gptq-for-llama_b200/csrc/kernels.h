@@ -12,7 +12,11 @@ struct QLinearArgs {
     gptq_qweight w;   // gate for the fused MLP
     gptq_qweight w2;  // up for the fused MLP (unused otherwise)
     bool dual;        // fused SwiGLU MLP
-    const void* bias;
+    const void* bias;      // fp16 [N] or null
+    const void* residual;  // fp16 [M, ldr] or null: out = residual + fp16(acc)   (decode engine)
+    int64_t ldr;
+    const void* norm_w;    // fp16 [K] or null: RMSNorm(x; norm_w, eps) fused in front of the product
+    float eps;
     void* out;
     int64_t ldo;
     int M;
@@ -25,6 +29,16 @@ struct QLinearArgs {
 cudaError_t launch_qlinear_generic(const QLinearArgs& a);
 cudaError_t launch_qlinear_transpose_generic(const void* g, int64_t ldg, const gptq_qweight& w, void* out, int64_t ldo, int M, cudaStream_t stream);
 cudaError_t launch_dequant(const gptq_qweight& w, void* out, int64_t ldo, cudaStream_t stream);
+
+// qmatvec.cu -- tuned int4 decode kernel (M <= 8, no act-order): stream-K over 2 CTAs/SM.
+struct SkinnyPlan {
+    int nslabs, nk, grid, max_contrib, seg_steps;
+    long long total_units;
+};
+SkinnyPlan plan_skinny(int M, int K, int N);
+size_t skinny_workspace_bytes(int M, int K, int N, bool dual);
+bool skinny_supported(const QLinearArgs& a);
+cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl);
 
 // elementwise.cu
 cudaError_t launch_rope(void* qk, int64_t token_stride, const int64_t* position_ids, int64_t pos_batch_stride, int bsz, int seq, int rows, int head_dim,

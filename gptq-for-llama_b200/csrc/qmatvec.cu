@@ -1,0 +1,544 @@
+// Skinny (decode) quantized matvec for int4, M <= 8: the batch-1 hot kernel.
+//
+// out[M,N] = x[M,K] . deq(W)   (matmul_248_kernel, quant/quant_linear.py:84-137 of the reference;
+// optional fused SwiGLU over two weights = fusedmatmul_248_kernel, quant/fused_mlp.py:84-168)
+//
+// Design (HBM-bound: 0.53 B/weight, ~2.8 issue slots per weight at 100 % of HBM):
+//  * Work = units of 4 packed rows (32 k) x 256 columns (4 KB of qweight, 1 KB contiguous per row).
+//    Units are numbered slab-major (slab = 256 columns) and split evenly over min(296, units) CTAs
+//    ("stream-K"): every SM streams the same number of bytes whatever the layer shape.
+//  * Each of the 8 warps owns a 32-column stripe of the slab and walks the k-steps of its CTA's range.
+//    A lane issues one 128-bit coalesced load per k-step (a warp reads 4 rows x 128 B) and keeps
+//    kPrefetch of them in flight in registers (2 CTAs/SM x 256 thr x 8 x 16 B = 64 KB in flight per SM).
+//  * Dequant is exact w.r.t. the reference: nibble -> fp16 by the 0x6400 magic-number trick (LOP3),
+//    (w - z) exactly in fp16 (HSUB2 / HFMA2), one HMUL2 by the fp16 scale (the reference's single fp16
+//    rounding), then fp16 x fp16 -> fp32 accumulation on the tensor pipe with the roles swapped
+//    (mma.m16n8k16: A = 16 output columns x 16 k of weights, B = 16 k x 8 batch rows of x).  This is the
+//    same arithmetic as the reference's tl.dot (fp16 operands, fp32 accumulate) at 1/4 of the issue
+//    slots a CUDA-core FMA loop needs; the k-order inside a run of 8 is permuted identically in x and W.
+//  * Partials of CTAs that share a slab go through a workspace; the last arriver (atomic counter, which
+//    it resets) reduces them in a fixed order -> deterministic results, no memset between launches.
+//  * Optional RMSNorm prologue (the reference's rms_norm_fwd_fused, quant/triton_norm.py:21-39) and
+//    residual epilogue so that a decoder layer needs 5 launches; PDL hooks (griddepcontrol) let the
+//    weight prefetch of kernel n+1 overlap the tail of kernel n.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gptq {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kSlabCols = 256;
+constexpr int kPrefetch = 8;
+
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_cg(const float* p) {
+    float r;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t h2_as_u32(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+__device__ __forceinline__ __half2 u32_as_h2(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Per-group dequant constants of one lane's 4 columns.
+struct GroupConst {
+    __half2 za01, za23;  // 1024 + z   for columns (0,1) and (2,3);  z = stored zero + 1
+    __half2 zb01, zb23;  // -(64 + z)
+    __half2 s01, s23;    // fp16 scales
+};
+
+// raw scale / zero words of one group for the lane's 4 columns
+struct GroupRaw {
+    uint2 s;     // 4 fp16 scales
+    uint32_t z;  // qzeros word holding the 4 nibbles
+};
+
+__device__ __forceinline__ GroupRaw load_group_raw(const __half* __restrict__ sc, const uint32_t* __restrict__ qz) {
+    GroupRaw r;
+    r.s = __ldg(reinterpret_cast<const uint2*>(sc));
+    r.z = __ldg(qz);
+    return r;
+}
+
+__device__ __forceinline__ void build_group_const(GroupConst& c, const GroupRaw& r, int zshift) {
+    const uint32_t zw = (r.z >> zshift) & 0xffffu;  // nibbles of columns col..col+3
+    const __half2 one = __float2half2_rn(1.0f), c960 = __float2half2_rn(960.0f);
+    uint32_t z01, z23;  // (1024+z0', 1024+z1'), (1024+z2', 1024+z3')
+    asm("lop3.b32 %0, %1, %2, 0x000f000f, 0xa8;" : "=r"(z01) : "r"(zw), "r"(zw << 12));  // (a | b) & c
+    asm("lop3.b32 %0, %1, %2, 0x000f000f, 0xa8;" : "=r"(z23) : "r"(zw >> 8), "r"(zw << 4));
+    z01 |= 0x64006400u;
+    z23 |= 0x64006400u;
+    c.za01 = __hadd2(u32_as_h2(z01), one);  // +1: zeros are stored minus one, the +1 is unmasked (quant_linear.py:120-121)
+    c.za23 = __hadd2(u32_as_h2(z23), one);
+    c.zb01 = __hsub2(c960, c.za01);  // 960 - (1024 + z) = -(64 + z)
+    c.zb23 = __hsub2(c960, c.za23);
+    c.s01 = u32_as_h2(r.s.x);
+    c.s23 = u32_as_h2(r.s.y);
+}
+
+template <int HI>
+__device__ __forceinline__ __half2 bcast(__half2 v) {  // folds into the .H0_H0 / .H1_H1 operand modifiers
+    return HI ? __half2half2(__high2half(v)) : __half2half2(__low2half(v));
+}
+
+// (q & mask) | 0x64006400 in ONE LOP3 (written as and+or the compiler emits two: LOP3 encodes a single immediate)
+template <uint32_t MASK>
+__device__ __forceinline__ __half2 nibbles_to_h2(uint32_t q) {
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, 0x64006400, 0xea;" : "=r"(r) : "r"(q), "n"(MASK));
+    return u32_as_h2(r);
+}
+
+template <int HI>
+__device__ __forceinline__ void dequant8(uint32_t q, __half2 za_pair, __half2 zb_pair, __half2 s_pair, uint32_t (&w)[4]) {
+    const __half2 za = bcast<HI>(za_pair), zb = bcast<HI>(zb_pair), s = bcast<HI>(s_pair);
+    const __half2 sixteenth = __float2half2_rn(0.0625f);
+    const uint32_t q8 = q >> 8;
+    const __half2 l0 = nibbles_to_h2<0x000f000fu>(q);   // 1024 + n
+    const __half2 h0 = nibbles_to_h2<0x00f000f0u>(q);   // 1024 + 16 n
+    const __half2 l1 = nibbles_to_h2<0x000f000fu>(q8);
+    const __half2 h1 = nibbles_to_h2<0x00f000f0u>(q8);
+    w[0] = h2_as_u32(__hmul2(__hsub2(l0, za), s));
+    w[1] = h2_as_u32(__hmul2(__hfma2(h0, sixteenth, zb), s));
+    w[2] = h2_as_u32(__hmul2(__hsub2(l1, za), s));
+    w[3] = h2_as_u32(__hmul2(__hfma2(h1, sixteenth, zb), s));
+}
+
+#ifdef GPTQ_TRACE
+}  // namespace
+__device__ unsigned long long* g_trace_buf = nullptr;
+namespace {
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot)                                                                                \
+    do {                                                                                           \
+        if (g_trace_buf != nullptr && threadIdx.x == 0) g_trace_buf[blockIdx.x * 8 + (slot)] = gtime(); \
+    } while (0)
+#else
+#define TRACE(slot) \
+    do {            \
+    } while (0)
+#endif
+
+struct SkinnyParams {
+    const __half* x;
+    int64_t ldx;
+    const uint32_t* qw[2];
+    const __half* sc[2];
+    const uint32_t* qz[2];
+    const __half* bias;      // [N] or null
+    const __half* residual;  // [M, ldr] or null: out = residual + fp16(acc)
+    int64_t ldr;
+    const __half* norm_w;  // [K] or null: x is RMS-normalised (weight norm_w, eps) before the product
+    float eps;
+    __half* out;
+    int64_t ldo;
+    int M, K, N, groupsize;
+    int nk;           // k-steps (32 k) per slab
+    int total_units;  // nslabs * nk
+    int max_contrib;
+    float* ws_partial;
+    int* ws_counter;
+    int xs_pitch;  // halves between x rows in shared memory
+};
+
+template <bool DUAL>
+__device__ __forceinline__ __half epilogue(const SkinnyParams& p, float a, float b, int m, int n) {
+    if constexpr (DUAL) {
+        return __float2half_rn(swiglu(a, b));
+    } else {
+        __half o = __float2half_rn(a);
+        if (p.bias != nullptr) o = __hadd(o, p.bias[n]);  // plain loads: __ldg may be speculated above the null check
+        if (p.residual != nullptr) o = __hadd(p.residual[(size_t)m * p.ldr + n], o);
+        return o;
+    }
+}
+
+template <bool DUAL>
+__global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyParams p) {
+    constexpr int NW = DUAL ? 2 : 1;
+    constexpr int PF = DUAL ? kPrefetch / 2 : kPrefetch;
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __half* xs = reinterpret_cast<__half*>(smem_raw);
+    __shared__ float red_s[kWarps];
+    __shared__ float rstd_s[8];
+    __shared__ int flag_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int nb = gridDim.x;
+    const long long U = p.total_units;
+    const int u_begin = (int)((blockIdx.x * U) / nb);
+    const int u_end = (int)(((blockIdx.x + 1) * U) / nb);
+    const int nk = p.nk, N = p.N;
+
+    grid_launch_dependents();
+    TRACE(0);
+
+    // ---- optional RMSNorm prologue: rstd per row, from the full x rows -------------------------
+    bool waited = false;
+    if (p.norm_w != nullptr) {
+        grid_dependency_wait();
+        waited = true;
+        for (int m = 0; m < p.M; ++m) {
+            const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.ldx);
+            float ss = 0.f;
+            for (int i = tid; i < p.K / 8; i += kThreads) {
+                const uint4 v = __ldg(xr + i);
+                const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 f = __half22float2(u32_as_h2(wv[j]));
+                    ss = fmaf(f.x, f.x, ss);
+                    ss = fmaf(f.y, f.y, ss);
+                }
+            }
+            ss = warp_sum(ss);
+            if (lane == 0) red_s[warp] = ss;
+            __syncthreads();
+            float tot = 0.f;
+#pragma unroll
+            for (int wv = 0; wv < kWarps; ++wv) tot += red_s[wv];
+            if (tid == 0) rstd_s[m] = 1.0f / sqrtf(tot / (float)p.K + p.eps);
+            __syncthreads();
+        }
+    }
+
+    int u = u_begin;
+    while (u < u_end) {
+        const int slab = u / nk;
+        const int ks0 = u - slab * nk;
+        const int nsteps = min(nk - ks0, u_end - u);
+        const int col0 = slab * kSlabCols;
+        const int ncols = min(kSlabCols, N - col0);
+        const bool active = warp * 32 < ncols;
+        const int col = col0 + warp * 32 + 4 * g;  // lane's first column
+
+        // ---- weight prefetch: independent of the previous kernel's output -----------------------
+        uint4 buf[NW][PF];
+        const uint4* wp[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            wp[w] = reinterpret_cast<const uint4*>(p.qw[w] + (size_t)(ks0 * 4 + t) * N + col);
+#pragma unroll
+            for (int i = 0; i < PF; ++i)
+                if (active && i < nsteps) buf[w][i] = ldg_stream(wp[w] + (size_t)i * N);  // +4 rows = N uint4
+        }
+        const int gs_steps = p.groupsize >> 5;  // k-steps per group
+        const int zshift = (col & 4) * 4;
+        GroupRaw raw[NW];
+        GroupConst gc[NW];
+        const __half* scp[NW];    // next group's scales / zeros for the lane's columns
+        const uint32_t* qzp[NW];
+        if (active) {
+            const int grp0 = (ks0 * 32) / p.groupsize;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                scp[w] = p.sc[w] + (size_t)grp0 * N + col;
+                qzp[w] = p.qz[w] + (size_t)grp0 * (N >> 3) + (col >> 3);
+                raw[w] = load_group_raw(scp[w], qzp[w]);
+                scp[w] += N;
+                qzp[w] += N >> 3;
+            }
+        }
+
+        TRACE(1);
+        // ---- stage x[k-range of this segment] into shared memory (normalised, k-permuted) -------
+        if (!waited) {
+            grid_dependency_wait();
+            waited = true;
+        }
+        __syncthreads();  // previous segment's readers are done with xs
+        {
+            const int kbeg = ks0 * 32;
+            const int chunks = nsteps * 4;  // 8-half chunks per row
+            for (int idx = tid; idx < p.M * chunks; idx += kThreads) {
+                const int m = idx / chunks, c = idx - m * chunks;
+                uint4 v = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)m * p.ldx + kbeg) + c);
+                if (p.norm_w != nullptr) {
+                    const uint4 nw = __ldg(reinterpret_cast<const uint4*>(p.norm_w + kbeg) + c);
+                    uint32_t xv[4] = {v.x, v.y, v.z, v.w};
+                    const uint32_t wv[4] = {nw.x, nw.y, nw.z, nw.w};
+                    const float rs = rstd_s[m];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 xf = __half22float2(u32_as_h2(xv[j])), wf = __half22float2(u32_as_h2(wv[j]));
+                        xv[j] = h2_as_u32(__floats2half2_rn(__fmul_rn(__fmul_rn(xf.x, rs), wf.x), __fmul_rn(__fmul_rn(xf.y, rs), wf.y)));
+                    }
+                    v = make_uint4(xv[0], xv[1], xv[2], xv[3]);
+                }
+                uint4 o;  // (k0,k4) (k1,k5) (k2,k6) (k3,k7): the order dequant8 produces
+                o.x = __byte_perm(v.x, v.z, 0x5410);
+                o.y = __byte_perm(v.x, v.z, 0x7632);
+                o.z = __byte_perm(v.y, v.w, 0x5410);
+                o.w = __byte_perm(v.y, v.w, 0x7632);
+                *reinterpret_cast<uint4*>(xs + (size_t)m * p.xs_pitch + c * 8) = o;
+            }
+        }
+        __syncthreads();
+
+        TRACE(2);
+        float acc[NW][2][4];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[w][h][i] = 0.f;
+
+        if (active) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) build_group_const(gc[w], raw[w], zshift);
+            int steps_left_in_grp = gs_steps - (ks0 % gs_steps);
+            if (steps_left_in_grp < nsteps) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    raw[w] = load_group_raw(scp[w], qzp[w]);
+                    scp[w] += N;
+                    qzp[w] += N >> 3;
+                }
+            }
+            const __half* xptr = xs + (size_t)(g < p.M ? g : 0) * p.xs_pitch + t * 8;
+            const uint4* pf[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) pf[w] = wp[w] + (size_t)PF * N;
+
+            for (int base = 0; base < nsteps; base += PF) {
+#pragma unroll
+                for (int i = 0; i < PF; ++i) {
+                    const int step = base + i;
+                    if (step < nsteps) {
+                        if (steps_left_in_grp == 0) {  // warp-uniform: entered a new group
+#pragma unroll
+                            for (int w = 0; w < NW; ++w) build_group_const(gc[w], raw[w], zshift);
+                            steps_left_in_grp = gs_steps;
+                            if (step + gs_steps < nsteps) {
+#pragma unroll
+                                for (int w = 0; w < NW; ++w) {
+                                    raw[w] = load_group_raw(scp[w], qzp[w]);
+                                    scp[w] += N;
+                                    qzp[w] += N >> 3;
+                                }
+                            }
+                        }
+                        --steps_left_in_grp;
+                        const uint4 xf = *reinterpret_cast<const uint4*>(xptr);
+                        xptr += 32;
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) {
+                            const uint32_t qv[4] = {buf[w][i].x, buf[w][i].y, buf[w][i].z, buf[w][i].w};
+                            uint32_t wf[4][4];
+                            dequant8<0>(qv[0], gc[w].za01, gc[w].zb01, gc[w].s01, wf[0]);
+                            dequant8<1>(qv[1], gc[w].za01, gc[w].zb01, gc[w].s01, wf[1]);
+                            dequant8<0>(qv[2], gc[w].za23, gc[w].zb23, gc[w].s23, wf[2]);
+                            dequant8<1>(qv[3], gc[w].za23, gc[w].zb23, gc[w].s23, wf[3]);
+                            // A rows g / g+8 = columns (col+0, col+1) then (col+2, col+3); two k16 halves each
+                            mma_16816(acc[w][0], wf[0][0], wf[1][0], wf[0][1], wf[1][1], xf.x, xf.y);
+                            mma_16816(acc[w][0], wf[0][2], wf[1][2], wf[0][3], wf[1][3], xf.z, xf.w);
+                            mma_16816(acc[w][1], wf[2][0], wf[3][0], wf[2][1], wf[3][1], xf.x, xf.y);
+                            mma_16816(acc[w][1], wf[2][2], wf[3][2], wf[2][3], wf[3][3], xf.z, xf.w);
+                            if (step + PF < nsteps) buf[w][i] = ldg_stream(pf[w]);  // refill the slot just consumed
+                            pf[w] += N;
+                        }
+                    }
+                }
+            }
+        }
+
+        TRACE(3);
+        // ---- flush this slab segment ---------------------------------------------------------------
+        // lane (g,t) holds batch rows m0 = 2t, m1 = 2t+1 of columns col..col+3:
+        //   acc[.][0][0|1] -> col+0, acc[.][0][2|3] -> col+1, acc[.][1][0|1] -> col+2, acc[.][1][2|3] -> col+3
+        const int first_cta = (int)((((long long)slab * nk + 1) * nb - 1) / U);
+        const int last_cta = (int)((((long long)slab * nk + nk) * nb - 1) / U);
+        const int ncontrib = last_cta - first_cta + 1;
+        if (ncontrib == 1) {
+            if (active) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int m = 2 * t + h;
+                    if (m < p.M) {
+                        __half o[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float a = acc[0][j >> 1][(j & 1) * 2 + h];
+                            const float b = DUAL ? acc[NW - 1][j >> 1][(j & 1) * 2 + h] : 0.f;
+                            o[j] = epilogue<DUAL>(p, a, b, m, col + j);
+                        }
+                        uint2 pk;
+                        pk.x = h2_as_u32(__halves2half2(o[0], o[1]));
+                        pk.y = h2_as_u32(__halves2half2(o[2], o[3]));
+                        *reinterpret_cast<uint2*>(p.out + (size_t)m * p.ldo + col) = pk;
+                    }
+                }
+            }
+        } else {
+            const int cidx = blockIdx.x - first_cta;
+            float* part = p.ws_partial + (size_t)(slab * p.max_contrib + cidx) * (NW * p.M * kSlabCols);
+            if (active) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int m = 2 * t + h;
+                        if (m < p.M)
+                            *reinterpret_cast<float4*>(part + (size_t)(w * p.M + m) * kSlabCols + warp * 32 + 4 * g) =
+                                make_float4(acc[w][0][h], acc[w][0][2 + h], acc[w][1][h], acc[w][1][2 + h]);
+                    }
+            }
+            __threadfence();
+            __syncthreads();
+            TRACE(4);
+            if (tid == 0) {
+                const int old = atomicAdd(p.ws_counter + slab, 1);
+                const int last = (old == ncontrib - 1);
+                if (last) p.ws_counter[slab] = 0;  // leave the workspace ready for the next launch
+                flag_s = last;
+            }
+            __syncthreads();
+            TRACE(5);
+            if (flag_s) {
+                __threadfence();
+                const float* sp = p.ws_partial + (size_t)slab * p.max_contrib * (NW * p.M * kSlabCols);
+                if (tid < ncols) {
+                    for (int m = 0; m < p.M; ++m) {
+                        float a = 0.f, b = 0.f;
+                        for (int c = 0; c < ncontrib; ++c) {  // fixed order: deterministic
+                            const float* pc = sp + (size_t)c * (NW * p.M * kSlabCols);
+                            a += ld_cg(pc + (size_t)m * kSlabCols + tid);
+                            if constexpr (DUAL) b += ld_cg(pc + (size_t)(p.M + m) * kSlabCols + tid);
+                        }
+                        p.out[(size_t)m * p.ldo + col0 + tid] = epilogue<DUAL>(p, a, b, m, col0 + tid);
+                    }
+                }
+            }
+        }
+        u += nsteps;
+        TRACE(6);
+    }
+}
+
+
+
+inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+SkinnyPlan plan_skinny(int M, int K, int N) {
+    SkinnyPlan pl{};
+    pl.nslabs = ceil_div(N, kSlabCols);
+    pl.nk = K / 32;
+    pl.total_units = (long long)pl.nslabs * pl.nk;
+    pl.grid = (int)(pl.total_units < 2LL * kNumSMs ? pl.total_units : 2LL * kNumSMs);
+    int maxc = 1;
+    for (int s = 0; s < pl.nslabs; ++s) {
+        const long long first = (((long long)s * pl.nk + 1) * pl.grid - 1) / pl.total_units;
+        const long long last = (((long long)s * pl.nk + pl.nk) * pl.grid - 1) / pl.total_units;
+        maxc = max(maxc, (int)(last - first + 1));
+    }
+    pl.max_contrib = maxc;
+    pl.seg_steps = (int)min((long long)pl.nk, ceil_div((int)pl.total_units, pl.grid) + 0LL);
+    return pl;
+}
+
+size_t skinny_workspace_bytes(int M, int K, int N, bool dual) {
+    if (M < 1 || M > 8 || K % 32 || N % 32) return 0;
+    const SkinnyPlan pl = plan_skinny(M, K, N);
+    const size_t counters = ((size_t)pl.nslabs * sizeof(int) + 255) & ~(size_t)255;
+    const size_t partial = (size_t)pl.nslabs * pl.max_contrib * (dual ? 2 : 1) * M * kSlabCols * sizeof(float);
+    return counters + partial;
+}
+
+bool skinny_supported(const QLinearArgs& a) {
+    const gptq_qweight& w = a.w;
+    if (w.bits != 4 || a.M < 1 || a.M > 8) return false;
+    if (w.groupsize <= 0 || w.groupsize % 32 != 0) return false;
+    if (!aligned_to(a.x, 16) || a.ldx % 8 != 0) return false;
+    if (!aligned_to(w.qweight, 16) || !aligned_to(w.scales, 8)) return false;
+    if (!aligned_to(a.out, 8) || a.ldo % 4 != 0) return false;
+    if (a.dual && (!aligned_to(a.w2.qweight, 16) || !aligned_to(a.w2.scales, 8))) return false;
+    if (a.norm_w != nullptr && !aligned_to(a.norm_w, 16)) return false;
+    const SkinnyPlan pl = plan_skinny(a.M, w.K, w.N);
+    const size_t smem = (size_t)a.M * (pl.seg_steps * 32 + 8) * sizeof(__half);
+    return smem <= 96 * 1024;
+}
+
+cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl) {
+    const gptq_qweight& w = a.w;
+    const SkinnyPlan pl = plan_skinny(a.M, w.K, w.N);
+    SkinnyParams p{};
+    p.x = reinterpret_cast<const __half*>(a.x);
+    p.ldx = a.ldx;
+    p.qw[0] = reinterpret_cast<const uint32_t*>(w.qweight);
+    p.sc[0] = reinterpret_cast<const __half*>(w.scales);
+    p.qz[0] = reinterpret_cast<const uint32_t*>(w.qzeros);
+    if (a.dual) {
+        p.qw[1] = reinterpret_cast<const uint32_t*>(a.w2.qweight);
+        p.sc[1] = reinterpret_cast<const __half*>(a.w2.scales);
+        p.qz[1] = reinterpret_cast<const uint32_t*>(a.w2.qzeros);
+    }
+    p.bias = reinterpret_cast<const __half*>(a.bias);
+    p.residual = reinterpret_cast<const __half*>(a.residual);
+    p.ldr = a.ldr;
+    p.norm_w = reinterpret_cast<const __half*>(a.norm_w);
+    p.eps = a.eps;
+    p.out = reinterpret_cast<__half*>(a.out);
+    p.ldo = a.ldo;
+    p.M = a.M; p.K = w.K; p.N = w.N; p.groupsize = w.groupsize;
+    p.nk = pl.nk;
+    p.total_units = (int)pl.total_units;
+    p.max_contrib = pl.max_contrib;
+    const size_t counters = ((size_t)pl.nslabs * sizeof(int) + 255) & ~(size_t)255;
+    p.ws_counter = reinterpret_cast<int*>(a.workspace);
+    p.ws_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.workspace) + counters);
+    // pitch: 64 B-odd multiple so that up to 8 x-rows map to distinct bank groups
+    int pitch = pl.seg_steps * 32;
+    if ((pitch / 32) % 2 == 0) pitch += 32;
+    p.xs_pitch = pitch;
+    const size_t smem = (size_t)a.M * pitch * sizeof(__half);
+
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(pl.grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = a.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    if (a.dual) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(qmatvec_int4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return cudaLaunchKernelEx(&cfg, qmatvec_int4_kernel<true>, p);
+    }
+    if (smem > 48 * 1024) cudaFuncSetAttribute(qmatvec_int4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaLaunchKernelEx(&cfg, qmatvec_int4_kernel<false>, p);
+}
+
+}  // namespace gptq
+
+#ifdef GPTQ_TRACE
+extern "C" int gptq_debug_set_trace(void* buf) {
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(buf);
+    return (int)cudaMemcpyToSymbol(gptq::g_trace_buf, &b, sizeof(b));
+}
+#endif

@@ -37,6 +37,7 @@ SIGNATURES = {
     'gptq_abi_version': (c_int, []),
     'gptq_strerror': (ctypes.c_char_p, [c_int]),
     'gptq_qlinear_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'gptq_fused_mlp_workspace_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
     'gptq_qlinear_fwd': (c_int, [c_void_p, c_int64, _QW, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     'gptq_fused_mlp_fwd': (c_int, [c_void_p, c_int64, _QW, _QW, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     'gptq_qlinear_transpose_fwd': (c_int, [c_void_p, c_int64, _QW, c_void_p, c_int64, c_int, c_void_p]),

@@ -87,6 +87,8 @@ def matmul248(input, qweight, scales, qzeros, g_idx, bits, maxq=None, bias=None,
     if input.shape[1] != w.K:
         raise ValueError(f'input has {input.shape[1]} features, weight expects {w.K}')
     M = input.shape[0]
+    if M == 0:
+        return torch.empty((0, w.N), device=input.device, dtype=torch.float16)
     with torch.cuda.device(input.device):
         out = torch.empty((M, w.N), device=input.device, dtype=torch.float16)
         ws, ws_bytes = _workspace(input.device, lib.gptq_qlinear_workspace_bytes(M, w.K, w.N, bits))
@@ -105,6 +107,8 @@ def transpose_matmul248(input, qweight, scales, qzeros, g_idx, bits, maxq=None, 
         input = input.contiguous()
     w = make_qweight(qweight, scales, qzeros, g_idx, bits, groupsize)
     M = input.shape[0]
+    if M == 0:
+        return torch.empty((0, w.K), device=input.device, dtype=torch.float16)
     with torch.cuda.device(input.device):
         out = torch.empty((M, w.K), device=input.device, dtype=torch.float16)
         check(lib.gptq_qlinear_transpose_fwd(input.data_ptr(), input.stride(0) if M > 1 else w.N, ctypes.byref(w), out.data_ptr(), w.K, M, _stream(input)))
@@ -121,9 +125,11 @@ def fused_mlp(x, gate, up, bits, groupsize: int = 0):
     wg = make_qweight(*gate, bits, groupsize)
     wu = make_qweight(*up, bits, groupsize)
     M = x.shape[0]
+    if M == 0:
+        return torch.empty((0, wg.N), device=x.device, dtype=torch.float16)
     with torch.cuda.device(x.device):
         out = torch.empty((M, wg.N), device=x.device, dtype=torch.float16)
-        ws, ws_bytes = _workspace(x.device, lib.gptq_qlinear_workspace_bytes(M, wg.K, 2 * wg.N, bits))
+        ws, ws_bytes = _workspace(x.device, lib.gptq_fused_mlp_workspace_bytes(M, wg.K, wg.N, bits))
         check(
             lib.gptq_fused_mlp_fwd(x.data_ptr(), x.stride(0) if M > 1 else wg.K, ctypes.byref(wg), ctypes.byref(wu), out.data_ptr(), wg.N, M,
                                    ws.data_ptr() if ws is not None else None, ws_bytes, _stream(x)))

@@ -67,8 +67,10 @@ int gptq_abi_version(void);
 const char* gptq_strerror(int status);
 
 /* Bytes of zero-initialised device workspace the M-row forward of a [K,N] layer may need
- * (split-K partials + arrival counters).  0 means no workspace is needed. */
+ * (split-K partials + arrival counters).  0 means no workspace is needed.  The workspace must be
+ * 256-byte aligned. */
 size_t gptq_qlinear_workspace_bytes(int M, int K, int N, int bits);
+size_t gptq_fused_mlp_workspace_bytes(int M, int K, int N, int bits);
 
 /* out[M,N] = x[M,K] . deq(W) (+ bias), fp16 in / fp32 accumulate / fp16 out.
  * Replaces matmul248 + matmul_248_kernel (quant/quant_linear.py:263-269, :72-137) and the
