@@ -32,6 +32,24 @@ class QWeight(ctypes.Structure):
 
 _QW = ctypes.POINTER(QWeight)
 
+
+class LlamaLayer(ctypes.Structure):
+    """struct gptq_llama_layer."""
+    _fields_ = [('qkv', QWeight), ('o', QWeight), ('gate', QWeight), ('up', QWeight), ('down', QWeight), ('input_norm', c_void_p), ('post_norm', c_void_p)]
+
+
+class LlamaModel(ctypes.Structure):
+    """struct gptq_llama_model."""
+    _fields_ = [('n_layers', c_int), ('hidden', c_int), ('n_heads', c_int), ('head_dim', c_int), ('intermediate', c_int), ('vocab', c_int), ('rms_eps', c_float),
+                ('rope_base', c_float), ('layers', ctypes.POINTER(LlamaLayer)), ('embed', c_void_p), ('final_norm', c_void_p), ('lm_head', c_void_p)]
+
+
+class LlamaState(ctypes.Structure):
+    """struct gptq_llama_state."""
+    _fields_ = [('batch', c_int), ('max_seq', c_int), ('k_cache', c_void_p), ('v_cache', c_void_p), ('tokens', c_void_p), ('positions', c_void_p),
+                ('logits', c_void_p), ('next_tokens', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_size_t)]
+
+
 # name -> (restype, argtypes); must list every symbol include/gptq_b200.h declares
 SIGNATURES = {
     'gptq_abi_version': (c_int, []),
@@ -48,6 +66,8 @@ SIGNATURES = {
     'gptq_unpack_qweight': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'gptq_unpack_qzeros': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'gptq_dequant': (c_int, [_QW, c_void_p, c_int64, c_void_p]),
+    'gptq_llama_scratch_bytes': (c_size_t, [ctypes.POINTER(LlamaModel), c_int, c_int]),
+    'gptq_llama_decode_step': (c_int, [ctypes.POINTER(LlamaModel), ctypes.POINTER(LlamaState), c_void_p]),
 }
 
 # gptq_status (include/gptq_b200.h)

@@ -1,0 +1,210 @@
+"""Decode engine host side: a GPTQ LLaMA decoded token by token on a static KV cache, the whole step
+captured once in a CUDA graph (gptq_llama_decode_step in include/gptq_b200.h).
+
+This is the B200-native replacement for the reference's per-token loop (llama.py:419-433 /
+model.generate in llama_inference.py:120): ~480 Python-dispatched launches and an O(n) torch.cat of
+the KV cache per token become one graph replay.  torch is used for device memory, streams and graph
+capture only.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import ops
+from ._lib import LlamaLayer, LlamaModel, LlamaState, QWeight, check, lib
+
+c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+
+LLAMA_SHAPES = {  # hidden, intermediate, layers, heads
+    '7b': (4096, 11008, 32, 32),
+    '13b': (5120, 13824, 40, 40),
+    '33b': (6656, 17920, 60, 52),
+    '65b': (8192, 22016, 80, 64),
+    'tiny': (256, 704, 2, 2),
+}
+
+
+class QLayerWeights:
+    """Packed tensors of one QuantLinear (kept alive by the engine) + the act-order probe result."""
+
+    def __init__(self, qweight, scales, qzeros, g_idx, bits, groupsize):
+        self.qweight, self.scales, self.qzeros, self.g_idx, self.bits = qweight.contiguous(), scales.contiguous(), qzeros.contiguous(), g_idx.contiguous(), bits
+        K = qweight.shape[0] * 32 // bits
+        self.g_idx = self.g_idx[:K].contiguous()
+        self.hint = groupsize if ops.is_trivial_g_idx(self.g_idx, groupsize) else 0
+
+    @classmethod
+    def from_module(cls, m):
+        return cls(m.qweight, m.scales, m.qzeros, m.g_idx, m.bits, m.groupsize)
+
+    def struct(self) -> QWeight:
+        return ops.make_qweight(self.qweight, self.scales, self.qzeros, self.g_idx, self.bits, self.hint)
+
+
+def random_qlayer(K, N, bits, groupsize, device, gen, act_order=False):
+    """Synthetic packed layer (SURVEY.md 8(d) perf fixture): uniform random fields, scales ~ U(1e-3, 1.1e-2)."""
+    G = math.ceil(K / groupsize)
+    if bits == 3:
+        from . import ops as _ops
+        qw = _ops.pack_qweight(torch.randint(0, 8, (K, N), device=device, generator=gen, dtype=torch.int32), 3)
+        qz = _ops.pack_qzeros(torch.randint(0, 8, (G, N), device=device, generator=gen, dtype=torch.int32), 3)
+    else:
+        qw = torch.randint(-2**31, 2**31 - 1, (K // 32 * bits, N), device=device, generator=gen, dtype=torch.int32)
+        qz = torch.randint(-2**31, 2**31 - 1, (G, N // 32 * bits), device=device, generator=gen, dtype=torch.int32)
+    s = (torch.rand(G, N, device=device, generator=gen) * 1e-2 + 1e-3).half()
+    g = (torch.arange(K, device=device) // groupsize).to(torch.int32)
+    if act_order:
+        perm = torch.randperm(K, device=device, generator=gen)
+        g = g[torch.argsort(perm)].contiguous()
+    return QLayerWeights(qw, s, qz, g, bits, groupsize)
+
+
+class LlamaDecoder:
+    """Owns the weights, the KV cache and the captured graph; `step()` decodes one token per sequence."""
+
+    def __init__(self, layers, embed, final_norm, lm_head, n_heads, rms_eps=1e-6, rope_base=10000.0, batch=1, max_seq=2048, use_graph=True):
+        self.dev = embed.device
+        self.layers = layers  # list of dicts: qkv, o, gate, up, down (QLayerWeights), input_norm, post_norm (fp16 tensors)
+        self.embed, self.final_norm, self.lm_head = embed.contiguous(), final_norm.contiguous(), lm_head.contiguous()
+        self.hidden = embed.shape[1]
+        self.vocab = embed.shape[0]
+        self.n_heads = n_heads
+        self.intermediate = layers[0]['gate'].qweight.shape[1]
+        self.batch, self.max_seq = batch, max_seq
+        with torch.cuda.device(self.dev):
+            self._layer_arr = (LlamaLayer * len(layers))()
+            for i, ly in enumerate(layers):
+                for name in ('qkv', 'o', 'gate', 'up', 'down'):
+                    setattr(self._layer_arr[i], name, ly[name].struct())
+                self._layer_arr[i].input_norm = ly['input_norm'].data_ptr()
+                self._layer_arr[i].post_norm = ly['post_norm'].data_ptr()
+            m = LlamaModel()
+            m.n_layers, m.hidden, m.n_heads, m.head_dim = len(layers), self.hidden, n_heads, self.hidden // n_heads
+            m.intermediate, m.vocab, m.rms_eps, m.rope_base = self.intermediate, self.vocab, rms_eps, rope_base
+            m.layers = ctypes.cast(self._layer_arr, ctypes.POINTER(LlamaLayer))
+            m.embed, m.final_norm, m.lm_head = self.embed.data_ptr(), self.final_norm.data_ptr(), self.lm_head.data_ptr()
+            self.model = m
+            cache_shape = (len(layers), batch, n_heads, max_seq, self.hidden // n_heads)
+            self.k_cache = torch.zeros(cache_shape, dtype=torch.float16, device=self.dev)
+            self.v_cache = torch.zeros(cache_shape, dtype=torch.float16, device=self.dev)
+            self.tokens = torch.zeros(batch, dtype=torch.int32, device=self.dev)
+            self.positions = torch.zeros(batch, dtype=torch.int32, device=self.dev)
+            self.logits = torch.zeros(batch, self.vocab, dtype=torch.float16, device=self.dev)
+            self.next_tokens = torch.zeros(batch, dtype=torch.int32, device=self.dev)
+            nbytes = lib.gptq_llama_scratch_bytes(ctypes.byref(m), batch, max_seq)
+            if nbytes == 0:
+                raise ValueError('unsupported decode configuration (batch must be 1..8)')
+            self.scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+            st = LlamaState()
+            st.batch, st.max_seq = batch, max_seq
+            st.k_cache, st.v_cache = self.k_cache.data_ptr(), self.v_cache.data_ptr()
+            st.tokens, st.positions = self.tokens.data_ptr(), self.positions.data_ptr()
+            st.logits, st.next_tokens = self.logits.data_ptr(), self.next_tokens.data_ptr()
+            st.scratch, st.scratch_bytes = self.scratch.data_ptr(), nbytes
+            self.state = st
+        self.n_launches = None
+        self.graph = None
+        self._stream = torch.cuda.Stream(self.dev)
+        if use_graph:
+            self._capture()
+
+    # ------------------------------------------------------------------------------------------
+    def _enqueue(self, stream):
+        check(lib.gptq_llama_decode_step(ctypes.byref(self.model), ctypes.byref(self.state), ctypes.c_void_p(stream.cuda_stream)))
+
+    def _capture(self):
+        with torch.cuda.device(self.dev):
+            torch.cuda.synchronize()
+            with torch.cuda.stream(self._stream):
+                self._enqueue(self._stream)  # warm-up outside capture (lazy module loading, func attributes)
+                self._stream.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self._stream):
+                    self._enqueue(self._stream)
+            self.graph = g
+            torch.cuda.synchronize()
+
+    def launches_per_step(self) -> int:
+        """Kernels of ours launched per decoded token: embed + 6 per layer + lm_head + argmax (general path: more)."""
+        extra = 0
+        for ly in self.layers:
+            for name, has_norm, has_res in (('qkv', 1, 0), ('o', 0, 1), ('gate', 1, 0), ('down', 0, 1)):
+                w = ly[name]
+                if not (w.bits == 4 and w.hint > 0 and w.hint % 32 == 0):
+                    extra += has_norm + has_res
+        return 1 + 6 * len(self.layers) + 2 + extra
+
+    def step(self, stream=None):
+        """Run one decode step on the tokens/positions currently in device memory."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue(stream or torch.cuda.current_stream(self.dev))
+
+    def reset(self):
+        self.positions.zero_()
+
+    @torch.no_grad()
+    def generate(self, prompt_ids, max_new_tokens):
+        """Greedy decode (batch 1): the prompt is fed token by token through the same decode step."""
+        assert self.batch == 1
+        out = list(prompt_ids)
+        self.reset()
+        tok = torch.empty(1, dtype=torch.int32, device=self.dev)
+        for i in range(len(prompt_ids) + max_new_tokens - 1):
+            if i < len(prompt_ids):
+                self.tokens.copy_(torch.tensor([prompt_ids[i]], dtype=torch.int32), non_blocking=False)
+            else:
+                self.tokens.copy_(tok)
+            self.positions.fill_(i)
+            self.step()
+            tok.copy_(self.next_tokens)
+            if i >= len(prompt_ids) - 1:
+                out.append(int(tok.item()))
+        return out
+
+
+def synthetic_llama(size='7b', bits=4, groupsize=128, act_order=False, vocab=32000, device='cuda:0', seed=0, n_layers=None, **kw):
+    """Random-init GPTQ LLaMA of the named size (no checkpoints are reachable offline): every layer has its
+    own distinct packed tensors so that a decode step streams the full model from HBM."""
+    hidden, inter, layers, heads = LLAMA_SHAPES[size]
+    layers = n_layers or layers
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    L = []
+    for _ in range(layers):
+        L.append(
+            dict(qkv=random_qlayer(hidden, 3 * hidden, bits, groupsize, dev, gen, act_order), o=random_qlayer(hidden, hidden, bits, groupsize, dev, gen, act_order),
+                 gate=random_qlayer(hidden, inter, bits, groupsize, dev, gen, act_order), up=random_qlayer(hidden, inter, bits, groupsize, dev, gen, act_order),
+                 down=random_qlayer(inter, hidden, bits, groupsize, dev, gen, act_order),
+                 input_norm=(torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half(),
+                 post_norm=(torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half()))
+    # q/k/v share their input, hence their act-order map (quant/fused_attn.py:180): nothing to do, qkv is one layer here
+    embed = (torch.randn(vocab, hidden, device=dev, generator=gen) * 0.5).half()
+    lm_head = (torch.randn(vocab, hidden, device=dev, generator=gen) * 0.02).half()
+    final_norm = (torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half()
+    return LlamaDecoder(L, embed, final_norm, lm_head, heads, **kw)
+
+
+def from_hf_quant_model(model, batch=1, max_seq=2048, **kw):
+    """Build a decoder from an HF LlamaForCausalLM that went through the reference's load_quant recipe with this
+    repo's quant package (make_quant_linear -> load_state_dict -> make_quant_attn / make_quant_norm / make_fused_mlp)."""
+    import quant
+    L = []
+    for layer in model.model.layers:
+        attn, mlp = layer.self_attn, layer.mlp
+        if not isinstance(attn, quant.QuantLlamaAttention):
+            raise ValueError('call quant.make_quant_attn(model) first')
+        if isinstance(mlp, quant.QuantLlamaMLP):
+            gate = QLayerWeights(mlp.gate_proj_qweight, mlp.gate_proj_scales, mlp.gate_proj_qzeros, mlp.gate_proj_g_idx, mlp.bits, mlp.groupsize)
+            up = QLayerWeights(mlp.up_proj_qweight, mlp.up_proj_scales, mlp.up_proj_qzeros, mlp.up_proj_g_idx, mlp.bits, mlp.groupsize)
+        else:
+            gate, up = QLayerWeights.from_module(mlp.gate_proj), QLayerWeights.from_module(mlp.up_proj)
+        L.append(
+            dict(qkv=QLayerWeights.from_module(attn.qkv_proj), o=QLayerWeights.from_module(attn.o_proj), gate=gate, up=up, down=QLayerWeights.from_module(mlp.down_proj),
+                 input_norm=layer.input_layernorm.weight.data.half().contiguous(), post_norm=layer.post_attention_layernorm.weight.data.half().contiguous()))
+    cfg = model.config
+    return LlamaDecoder(L, model.model.embed_tokens.weight.data.half(), model.model.norm.weight.data.half().contiguous(), model.lm_head.weight.data.half(),
+                        cfg.num_attention_heads, rms_eps=cfg.rms_norm_eps, rope_base=getattr(cfg, 'rope_theta', 10000.0) or 10000.0, batch=batch, max_seq=max_seq, **kw)

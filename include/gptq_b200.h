@@ -112,6 +112,48 @@ int gptq_unpack_qzeros(const int32_t* qzeros, int32_t* zeros_m1, int G, int N, i
  * (quant/quant_linear.py:114-128).  Used by tests and by load-time validation. */
 int gptq_dequant(const gptq_qweight* w, void* out, int64_t ldo, gptq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Decode engine: one token step of a GPTQ LLaMA on a static KV cache, i.e. the
+ * body of the reference's per-token benchmark loop (llama.py:419-433) -- LlamaDecoderLayer.forward over
+ * TritonLlamaRMSNorm, QuantLlamaAttention.forward (quant/fused_attn.py:117-161: fused qkv, in-place RoPE,
+ * KV append, SDPA, o_proj) and QuantLlamaMLP.forward (quant/fused_mlp.py:203-218) -- as a fixed sequence of
+ * kernel launches on `stream`: no allocation, no host sync, position and token ids are read from device
+ * memory, so the whole step can be captured once in a CUDA graph and replayed per token.
+ * Per layer: [RMSNorm + qkv matvec] -> [RoPE + KV append + split-KV attention] -> [combine] ->
+ * [o_proj + residual] -> [RMSNorm + gate/up matvec + SwiGLU] -> [down_proj + residual].
+ */
+typedef struct gptq_llama_layer {
+    gptq_qweight qkv;  /* fused q|k|v: N = 3*hidden (quant/fused_attn.py:177-181) */
+    gptq_qweight o, gate, up, down;
+    const void* input_norm;  /* fp16 [hidden] */
+    const void* post_norm;   /* fp16 [hidden] */
+} gptq_llama_layer;
+
+typedef struct gptq_llama_model {
+    int n_layers, hidden, n_heads, head_dim, intermediate, vocab;
+    float rms_eps, rope_base;
+    const gptq_llama_layer* layers; /* HOST array of n_layers entries (device pointers inside) */
+    const void* embed;      /* fp16 [vocab, hidden] */
+    const void* final_norm; /* fp16 [hidden] */
+    const void* lm_head;    /* fp16 [vocab, hidden] (never quantized, llama_inference.py:46-48) */
+} gptq_llama_model;
+
+typedef struct gptq_llama_state {
+    int batch;   /* sequences decoded in lock-step, 1..8 */
+    int max_seq; /* KV-cache capacity in tokens */
+    void* k_cache; /* fp16 [n_layers, batch, n_heads, max_seq, head_dim], keys stored after RoPE */
+    void* v_cache; /* fp16, same shape */
+    const int32_t* tokens;    /* device int32 [batch]: token ids of this step */
+    const int32_t* positions; /* device int32 [batch]: position of this step's token (= tokens already cached) */
+    void* logits;             /* fp16 [batch, vocab] out */
+    int32_t* next_tokens;     /* device int32 [batch] out: argmax of logits, or NULL to skip */
+    void* scratch;            /* device, gptq_llama_scratch_bytes() bytes, zero-filled once */
+    size_t scratch_bytes;
+} gptq_llama_state;
+
+size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int batch, int max_seq);
+int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_llama_state* state, gptq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
