@@ -6,6 +6,8 @@
 // re-copies the whole KV cache every token (torch.cat, fused_attn.py:142-143) and issues ~15 Python-
 // dispatched launches per layer; here the cache is static, RoPE + KV append + attention are one kernel,
 // the two RMSNorms and the two residual adds are fused into the matvecs, and nothing touches the host.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,8 +18,30 @@ constexpr int kAttnChunk = 256;    // keys per attention CTA
 constexpr int kAttnThreads = 128;  // 16 groups of 8 lanes; a group owns one key at a time
 constexpr int kHeadDim = 128;
 
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Launch with the programmatic-dependent-launch attribute: the kernel may start while its predecessor drains; every
+// kernel calls pdl_wait() before it touches anything another kernel produces or still reads.
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("GPTQ_NO_PDL") == nullptr ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __global__ void embed_kernel(const __half* __restrict__ embed, const int32_t* __restrict__ tokens, __half* __restrict__ x, int hidden) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tokens[b] * hidden);
     uint4* dst = reinterpret_cast<uint4*>(x + (size_t)b * hidden);
     for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -25,6 +49,8 @@ __global__ void embed_kernel(const __half* __restrict__ embed, const int32_t* __
 
 __global__ void residual_add_kernel(__half* __restrict__ x, const __half* __restrict__ y, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (i < n) x[i] = __hadd(x[i], y[i]);
 }
 
@@ -36,6 +62,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const __half*
                                                                    __half* __restrict__ v_cache, const int32_t* __restrict__ positions, int n_heads, int max_seq,
                                                                    int batch, float inv_base, float scale, float* __restrict__ part, int nsplit) {
     const int head = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
+    pdl_trigger();
+    pdl_wait();
     const int pos = positions[b];
     const int T = pos + 1;
     const int c0 = split * kAttnChunk;
@@ -157,6 +185,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const __half*
 __global__ void __launch_bounds__(kHeadDim) attn_combine_kernel(const float* __restrict__ part, const int32_t* __restrict__ positions, __half* __restrict__ out,
                                                                 int hidden, int n_heads, int nsplit) {
     const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const int nvalid = min(nsplit, positions[b] / kAttnChunk + 1);
     const float* src = part + ((size_t)(b * n_heads + head) * nsplit) * (kHeadDim + 2);
     float M = -INFINITY;
@@ -180,6 +210,8 @@ __global__ void __launch_bounds__(256) lm_head_kernel(const __half* __restrict__
     __half* xs = reinterpret_cast<__half*>(smem_raw);  // [batch][hidden] normalised
     __shared__ float red[8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
     for (int b = 0; b < batch; ++b) {
         const __half2* xr = reinterpret_cast<const __half2*>(x + (size_t)b * hidden);
         float ss = 0.f;
@@ -239,6 +271,8 @@ __global__ void __launch_bounds__(256) lm_head_kernel(const __half* __restrict__
 
 __global__ void __launch_bounds__(1024) argmax_kernel(const __half* __restrict__ logits, int vocab, int32_t* __restrict__ out) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const __half* row = logits + (size_t)b * vocab;
     float best = -INFINITY;
     int idx = 0x7fffffff;
@@ -325,7 +359,7 @@ cudaError_t engine_linear(const gptq_qweight& w, const gptq_qweight* w2, const v
     if (w2) a.w2 = *w2;
     a.norm_w = norm_w; a.eps = eps; a.residual = residual; a.ldr = ldo; a.out = out; a.ldo = ldo; a.M = M;
     a.workspace = scratch + L.ws; a.ws_bytes = L.ws_bytes; a.stream = stream;
-    if (skinny_supported(a)) return launch_qlinear_skinny(a, false);
+    if (skinny_supported(a)) return launch_qlinear_skinny(a, true);
     // general path (act-order, other bit widths): separate norm / generic product / residual add
     QLinearArgs g = a;
     g.norm_w = nullptr;
@@ -345,8 +379,8 @@ cudaError_t engine_linear(const gptq_qweight& w, const gptq_qweight* w2, const v
     if (residual != nullptr) {
         // residual and out are the same buffer in the engine (in-place x += f(x))
         const int n = M * w.N;
-        residual_add_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(reinterpret_cast<__half*>(out), reinterpret_cast<const __half*>(scratch + L.tmp), n);
-        return cudaGetLastError();
+        return launch_pdl(residual_add_kernel, dim3(ceil_div(n, 256)), dim3(256), 0, stream, reinterpret_cast<__half*>(out),
+                          reinterpret_cast<const __half*>(scratch + L.tmp), n);
     }
     return cudaSuccess;
 }
@@ -398,17 +432,14 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
         if ((expr) != cudaSuccess) return GPTQ_ERR_CUDA; \
     } while (0)
 
-    embed_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const __half*>(m.embed), st->tokens, x, H);
-    GPTQ_TRY(cudaGetLastError());
+    GPTQ_TRY(launch_pdl(embed_kernel, dim3(B), dim3(256), 0, stream, reinterpret_cast<const __half*>(m.embed), st->tokens, x, H));
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         GPTQ_TRY(engine_linear(ly.qkv, nullptr, x, H, ly.input_norm, m.rms_eps, nullptr, qkv, 3 * H, B, sc, L, stream));
-        attn_decode_kernel<<<dim3(m.n_heads, L.nsplit, B), kAttnThreads, 0, stream>>>(qkv, H, reinterpret_cast<__half*>(st->k_cache) + l * layer_stride,
-                                                                                      reinterpret_cast<__half*>(st->v_cache) + l * layer_stride, st->positions,
-                                                                                      m.n_heads, st->max_seq, B, inv_base, scale, part, L.nsplit);
-        GPTQ_TRY(cudaGetLastError());
-        attn_combine_kernel<<<dim3(m.n_heads, B), kHeadDim, 0, stream>>>(part, st->positions, attn, H, m.n_heads, L.nsplit);
-        GPTQ_TRY(cudaGetLastError());
+        GPTQ_TRY(launch_pdl(attn_decode_kernel, dim3(m.n_heads, L.nsplit, B), dim3(kAttnThreads), 0, stream, qkv, H,
+                            reinterpret_cast<__half*>(st->k_cache) + l * layer_stride, reinterpret_cast<__half*>(st->v_cache) + l * layer_stride, st->positions,
+                            m.n_heads, st->max_seq, B, inv_base, scale, part, L.nsplit));
+        GPTQ_TRY(launch_pdl(attn_combine_kernel, dim3(m.n_heads, B), dim3(kHeadDim), 0, stream, part, st->positions, attn, H, m.n_heads, L.nsplit));
         GPTQ_TRY(engine_linear(ly.o, nullptr, attn, H, nullptr, 0.f, x, x, H, B, sc, L, stream));
         GPTQ_TRY(engine_linear(ly.gate, &ly.up, x, H, ly.post_norm, m.rms_eps, nullptr, h, m.intermediate, B, sc, L, stream));
         GPTQ_TRY(engine_linear(ly.down, nullptr, h, m.intermediate, nullptr, 0.f, x, x, H, B, sc, L, stream));
@@ -417,17 +448,16 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
         const size_t smem = (size_t)B * H * sizeof(__half);
         const int grid = min(ceil_div(m.vocab, 8), kNumSMs * 8);
         if (smem > 48 * 1024) GPTQ_TRY(cudaFuncSetAttribute(lm_head_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const __half* fn = reinterpret_cast<const __half*>(m.final_norm);
+        const __half* lw = reinterpret_cast<const __half*>(m.lm_head);
+        __half* lg = reinterpret_cast<__half*>(st->logits);
         if (B == 1)
-            lm_head_kernel<1><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __half*>(m.final_norm), m.rms_eps, reinterpret_cast<const __half*>(m.lm_head),
-                                                           reinterpret_cast<__half*>(st->logits), H, m.vocab, B);
+            GPTQ_TRY(launch_pdl(lm_head_kernel<1>, dim3(grid), dim3(256), smem, stream, (const __half*)x, fn, m.rms_eps, lw, lg, H, m.vocab, B));
         else
-            lm_head_kernel<8><<<grid, 256, smem, stream>>>(x, reinterpret_cast<const __half*>(m.final_norm), m.rms_eps, reinterpret_cast<const __half*>(m.lm_head),
-                                                           reinterpret_cast<__half*>(st->logits), H, m.vocab, B);
-        GPTQ_TRY(cudaGetLastError());
+            GPTQ_TRY(launch_pdl(lm_head_kernel<8>, dim3(grid), dim3(256), smem, stream, (const __half*)x, fn, m.rms_eps, lw, lg, H, m.vocab, B));
     }
     if (st->next_tokens != nullptr) {
-        argmax_kernel<<<B, 1024, 0, stream>>>(reinterpret_cast<const __half*>(st->logits), m.vocab, st->next_tokens);
-        GPTQ_TRY(cudaGetLastError());
+        GPTQ_TRY(launch_pdl(argmax_kernel, dim3(B), dim3(1024), 0, stream, reinterpret_cast<const __half*>(st->logits), m.vocab, st->next_tokens));
     }
 #undef GPTQ_TRY
     return GPTQ_OK;

@@ -8,8 +8,14 @@
 //    Units are numbered slab-major (slab = 256 columns) and split evenly over min(296, units) CTAs
 //    ("stream-K"): every SM streams the same number of bytes whatever the layer shape.
 //  * Each of the 8 warps owns a 32-column stripe of the slab and walks the k-steps of its CTA's range.
-//    A lane issues one 128-bit coalesced load per k-step (a warp reads 4 rows x 128 B) and keeps
-//    kPrefetch of them in flight in registers (2 CTAs/SM x 256 thr x 8 x 16 B = 64 KB in flight per SM).
+//    Weights are staged global -> shared memory by 16-byte asynchronous copies (cp.async / LDGSTS, L1 bypass):
+//    a lane keeps 16 of them in flight in a private shared-memory ring (2 CTAs/SM x 8 warps x 8 KB = 128 KB in
+//    flight per SM) and later reads back exactly the 16 bytes it copied, so the streaming loop has no barriers
+//    and no bank conflicts.  The ring runs ahead across slab boundaries and is primed BEFORE
+//    griddepcontrol.wait: under programmatic dependent launch the weights of kernel n+1 stream while kernel n
+//    reduces.  (A TMA-tiled variant was measured: 512-byte boxes gave the same bandwidth at +60 % instructions.)
+//  * The loop is rolled and the kernel is ~10 KB of SASS: a 38 KB unrolled build spent as long fetching
+//    instructions as weights (an SM streams only ~56 KB of weights per 4096x4096 layer).
 //  * Dequant is exact w.r.t. the reference: nibble -> fp16 by the 0x6400 magic-number trick (LOP3),
 //    (w - z) exactly in fp16 (HSUB2 / HFMA2), one HMUL2 by the fp16 scale (the reference's single fp16
 //    rounding), then fp16 x fp16 -> fp32 accumulation on the tensor pipe with the roles swapped
@@ -21,6 +27,8 @@
 //  * Optional RMSNorm prologue (the reference's rms_norm_fwd_fused, quant/triton_norm.py:21-39) and
 //    residual epilogue so that a decoder layer needs 5 launches; PDL hooks (griddepcontrol) let the
 //    weight prefetch of kernel n+1 overlap the tail of kernel n.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,11 +39,20 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kSlabCols = 256;
-constexpr int kPrefetch = 8;
+constexpr int kRingBytesPerWarp = 8192;  // 16 stages x 512 B (8 stages x 1 KB for the dual kernel)
 
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
     return r;
 }
 __device__ __forceinline__ float ld_cg(const float* p) {
@@ -43,6 +60,7 @@ __device__ __forceinline__ float ld_cg(const float* p) {
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(r) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -175,29 +193,67 @@ __device__ __forceinline__ __half epilogue(const SkinnyParams& p, float a, float
 template <bool DUAL>
 __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyParams p) {
     constexpr int NW = DUAL ? 2 : 1;
-    constexpr int PF = DUAL ? kPrefetch / 2 : kPrefetch;
+    constexpr int STAGE_BYTES = NW * 512;
+    constexpr int NST = kRingBytesPerWarp / STAGE_BYTES;  // ring depth in k-steps: 16 (8 for the dual kernel)
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __half* xs = reinterpret_cast<__half*>(smem_raw);
     __shared__ float red_s[kWarps];
     __shared__ float rstd_s[8];
-    __shared__ int flag_s;
+    __shared__ int pend_slab_s[2], pend_nc_s[2], pend_last_s[2];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int nb = gridDim.x;
-    const long long U = p.total_units;
+    const unsigned nb = gridDim.x;
+    const unsigned U = (unsigned)p.total_units;  // U * (nb + 1) < 2^31 (checked on the host)
     const int u_begin = (int)((blockIdx.x * U) / nb);
     const int u_end = (int)(((blockIdx.x + 1) * U) / nb);
     const int nk = p.nk, N = p.N;
 
-    grid_launch_dependents();
-    TRACE(0);
+    // shared memory: [per-warp weight rings: kWarps x 8 KB][x staging]
+    __half* xs = reinterpret_cast<__half*>(smem_raw + kWarps * kRingBytesPerWarp);
+    const uint32_t ring_lo = smem_u32(smem_raw) + warp * kRingBytesPerWarp + lane * 16;  // this lane's slot of stage 0
+    const uint32_t ring_hi = ring_lo + kRingBytesPerWarp;
 
-    // ---- optional RMSNorm prologue: rstd per row, from the full x rows -------------------------
-    bool waited = false;
-    if (p.norm_w != nullptr) {
-        grid_dependency_wait();
-        waited = true;
+    TRACE(0);
+    // ---- producer cursor: this lane's next 16 B of weights (row t of the next k-step, columns 4g..4g+3 of its stripe) ----
+    const int first_slab = u_begin / nk;
+    const int first_ks = u_begin - first_slab * nk;
+    const uint4* gp[NW];
+    {
+        const size_t off = (size_t)(first_ks * 4 + t) * N + first_slab * kSlabCols + warp * 32 + 4 * g;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) gp[w] = reinterpret_cast<const uint4*>(p.qw[w] + off);
+    }
+    const long long wrap = (long long)(kSlabCols / 4) - (long long)nk * N;  // next slab, back to row 0 (in uint4 units)
+    int p_left = u_end - u_begin;                                          // k-steps not yet requested
+    int p_rows_left = nk - first_ks;                                       // ... of them in the current slab
+    int p_colw = first_slab * kSlabCols + warp * 32;                       // first column of the warp's stripe
+    uint32_t slot = ring_lo;                                               // ring cursor (shared by producer and consumer)
+    auto produce = [&](uint32_t dst) {
+        if (p_left > 0) {
+            if (p_colw < N) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) cp_async16(dst + w * 512, gp[w]);
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) gp[w] += N;  // 4 packed rows down
+            --p_left;
+            if (--p_rows_left == 0) {
+#pragma unroll
+                for (int w = 0; w < NW; ++w) gp[w] += wrap;
+                p_rows_left = nk;
+                p_colw += kSlabCols;
+            }
+        }
+        cp_async_commit();  // always commit (possibly empty) so that wait_group counts stay aligned
+    };
+#pragma unroll 1
+    for (int s = 0; s < NST; ++s) produce(ring_lo + s * STAGE_BYTES);  // prime the ring: independent of the previous kernel
+    grid_launch_dependents();
+    TRACE(1);
+
+    // ---- everything below may depend on the previous kernel's output ---------------------------------
+    grid_dependency_wait();
+    if (p.norm_w != nullptr) {  // RMSNorm prologue: rstd per row from the full x rows
         for (int m = 0; m < p.M; ++m) {
             const uint4* xr = reinterpret_cast<const uint4*>(p.x + (size_t)m * p.ldx);
             float ss = 0.f;
@@ -222,7 +278,9 @@ __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyP
         }
     }
 
+    int npend = 0;
     int u = u_begin;
+#pragma unroll 1
     while (u < u_end) {
         const int slab = u / nk;
         const int ks0 = u - slab * nk;
@@ -232,16 +290,6 @@ __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyP
         const bool active = warp * 32 < ncols;
         const int col = col0 + warp * 32 + 4 * g;  // lane's first column
 
-        // ---- weight prefetch: independent of the previous kernel's output -----------------------
-        uint4 buf[NW][PF];
-        const uint4* wp[NW];
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            wp[w] = reinterpret_cast<const uint4*>(p.qw[w] + (size_t)(ks0 * 4 + t) * N + col);
-#pragma unroll
-            for (int i = 0; i < PF; ++i)
-                if (active && i < nsteps) buf[w][i] = ldg_stream(wp[w] + (size_t)i * N);  // +4 rows = N uint4
-        }
         const int gs_steps = p.groupsize >> 5;  // k-steps per group
         const int zshift = (col & 4) * 4;
         GroupRaw raw[NW];
@@ -260,12 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyP
             }
         }
 
-        TRACE(1);
         // ---- stage x[k-range of this segment] into shared memory (normalised, k-permuted) -------
-        if (!waited) {
-            grid_dependency_wait();
-            waited = true;
-        }
         __syncthreads();  // previous segment's readers are done with xs
         {
             const int kbeg = ks0 * 32;
@@ -316,50 +359,52 @@ __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyP
                     qzp[w] += N >> 3;
                 }
             }
-            const __half* xptr = xs + (size_t)(g < p.M ? g : 0) * p.xs_pitch + t * 8;
-            const uint4* pf[NW];
-#pragma unroll
-            for (int w = 0; w < NW; ++w) pf[w] = wp[w] + (size_t)PF * N;
+            uint32_t xaddr = smem_u32(xs) + ((g < p.M ? g : 0) * p.xs_pitch + t * 8) * 2;
 
-            for (int base = 0; base < nsteps; base += PF) {
+#pragma unroll 1
+            for (int step = 0; step < nsteps; ++step) {
+                if (steps_left_in_grp == 0) {  // warp-uniform: entered a new group
 #pragma unroll
-                for (int i = 0; i < PF; ++i) {
-                    const int step = base + i;
-                    if (step < nsteps) {
-                        if (steps_left_in_grp == 0) {  // warp-uniform: entered a new group
-#pragma unroll
-                            for (int w = 0; w < NW; ++w) build_group_const(gc[w], raw[w], zshift);
-                            steps_left_in_grp = gs_steps;
-                            if (step + gs_steps < nsteps) {
-#pragma unroll
-                                for (int w = 0; w < NW; ++w) {
-                                    raw[w] = load_group_raw(scp[w], qzp[w]);
-                                    scp[w] += N;
-                                    qzp[w] += N >> 3;
-                                }
-                            }
-                        }
-                        --steps_left_in_grp;
-                        const uint4 xf = *reinterpret_cast<const uint4*>(xptr);
-                        xptr += 32;
+                    for (int w = 0; w < NW; ++w) build_group_const(gc[w], raw[w], zshift);
+                    steps_left_in_grp = gs_steps;
+                    if (step + gs_steps < nsteps) {
 #pragma unroll
                         for (int w = 0; w < NW; ++w) {
-                            const uint32_t qv[4] = {buf[w][i].x, buf[w][i].y, buf[w][i].z, buf[w][i].w};
-                            uint32_t wf[4][4];
-                            dequant8<0>(qv[0], gc[w].za01, gc[w].zb01, gc[w].s01, wf[0]);
-                            dequant8<1>(qv[1], gc[w].za01, gc[w].zb01, gc[w].s01, wf[1]);
-                            dequant8<0>(qv[2], gc[w].za23, gc[w].zb23, gc[w].s23, wf[2]);
-                            dequant8<1>(qv[3], gc[w].za23, gc[w].zb23, gc[w].s23, wf[3]);
-                            // A rows g / g+8 = columns (col+0, col+1) then (col+2, col+3); two k16 halves each
-                            mma_16816(acc[w][0], wf[0][0], wf[1][0], wf[0][1], wf[1][1], xf.x, xf.y);
-                            mma_16816(acc[w][0], wf[0][2], wf[1][2], wf[0][3], wf[1][3], xf.z, xf.w);
-                            mma_16816(acc[w][1], wf[2][0], wf[3][0], wf[2][1], wf[3][1], xf.x, xf.y);
-                            mma_16816(acc[w][1], wf[2][2], wf[3][2], wf[2][3], wf[3][3], xf.z, xf.w);
-                            if (step + PF < nsteps) buf[w][i] = ldg_stream(pf[w]);  // refill the slot just consumed
-                            pf[w] += N;
+                            raw[w] = load_group_raw(scp[w], qzp[w]);
+                            scp[w] += N;
+                            qzp[w] += N >> 3;
                         }
                     }
                 }
+                --steps_left_in_grp;
+                const uint4 xf = lds128(xaddr);
+                xaddr += 64;
+                cp_async_wait<NST - 1>();  // this lane's oldest copy has landed (a lane only reads bytes it copied itself)
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const uint4 q = lds128(slot + w * 512);
+                    uint32_t wf[4][4];
+                    dequant8<0>(q.x, gc[w].za01, gc[w].zb01, gc[w].s01, wf[0]);
+                    dequant8<1>(q.y, gc[w].za01, gc[w].zb01, gc[w].s01, wf[1]);
+                    dequant8<0>(q.z, gc[w].za23, gc[w].zb23, gc[w].s23, wf[2]);
+                    dequant8<1>(q.w, gc[w].za23, gc[w].zb23, gc[w].s23, wf[3]);
+                    // A rows g / g+8 = columns (col+0, col+1) then (col+2, col+3); two k16 halves each
+                    mma_16816(acc[w][0], wf[0][0], wf[1][0], wf[0][1], wf[1][1], xf.x, xf.y);
+                    mma_16816(acc[w][0], wf[0][2], wf[1][2], wf[0][3], wf[1][3], xf.z, xf.w);
+                    mma_16816(acc[w][1], wf[2][0], wf[3][0], wf[2][1], wf[3][1], xf.x, xf.y);
+                    mma_16816(acc[w][1], wf[2][2], wf[3][2], wf[2][3], wf[3][3], xf.z, xf.w);
+                }
+                produce(slot);  // the slot's registers have been consumed by the mma's above: refill it NST steps ahead
+                slot += STAGE_BYTES;
+                if (slot == ring_hi) slot = ring_lo;
+            }
+        } else {
+            // this warp owns no columns in the (ragged) last slab: keep its cursors in step
+#pragma unroll 1
+            for (int step = 0; step < nsteps; ++step) {
+                produce(slot);
+                slot += STAGE_BYTES;
+                if (slot == ring_hi) slot = ring_lo;
             }
         }
 
@@ -367,8 +412,8 @@ __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyP
         // ---- flush this slab segment ---------------------------------------------------------------
         // lane (g,t) holds batch rows m0 = 2t, m1 = 2t+1 of columns col..col+3:
         //   acc[.][0][0|1] -> col+0, acc[.][0][2|3] -> col+1, acc[.][1][0|1] -> col+2, acc[.][1][2|3] -> col+3
-        const int first_cta = (int)((((long long)slab * nk + 1) * nb - 1) / U);
-        const int last_cta = (int)((((long long)slab * nk + nk) * nb - 1) / U);
+        const int first_cta = (int)(((unsigned)(slab * nk + 1) * nb - 1) / U);
+        const int last_cta = (int)(((unsigned)(slab * nk + nk) * nb - 1) / U);
         const int ncontrib = last_cta - first_cta + 1;
         if (ncontrib == 1) {
             if (active) {
@@ -404,39 +449,65 @@ __global__ void __launch_bounds__(kThreads, 2) qmatvec_int4_kernel(const SkinnyP
                                 make_float4(acc[w][0][h], acc[w][0][2 + h], acc[w][1][h], acc[w][1][2 + h]);
                     }
             }
-            __threadfence();
-            __syncthreads();
-            TRACE(4);
+            // only the first and the last segment of a CTA can be shared with other CTAs: at most two pending slabs
             if (tid == 0) {
-                const int old = atomicAdd(p.ws_counter + slab, 1);
-                const int last = (old == ncontrib - 1);
-                if (last) p.ws_counter[slab] = 0;  // leave the workspace ready for the next launch
-                flag_s = last;
+                pend_slab_s[npend] = slab;
+                pend_nc_s[npend] = ncontrib;
             }
-            __syncthreads();
-            TRACE(5);
-            if (flag_s) {
-                __threadfence();
-                const float* sp = p.ws_partial + (size_t)slab * p.max_contrib * (NW * p.M * kSlabCols);
-                if (tid < ncols) {
-                    for (int m = 0; m < p.M; ++m) {
-                        float a = 0.f, b = 0.f;
-                        for (int c = 0; c < ncontrib; ++c) {  // fixed order: deterministic
+            ++npend;
+        }
+        u += nsteps;
+    }
+
+    // ---- one release / arrive / acquire round for all shared slabs of this CTA -------------------------
+    if (npend > 0) {
+        fence_acq_rel_gpu();  // release: this thread's partial stores
+        __syncthreads();
+        TRACE(4);
+        if (tid < npend) {
+            const int old = atomicAdd(p.ws_counter + pend_slab_s[tid], 1);
+            const int last = (old == pend_nc_s[tid] - 1);
+            if (last) p.ws_counter[pend_slab_s[tid]] = 0;  // leave the workspace ready for the next launch
+            pend_last_s[tid] = last;
+        }
+        __syncthreads();
+        TRACE(5);
+        for (int i = 0; i < npend; ++i) {
+            if (!pend_last_s[i]) continue;
+            fence_acq_rel_gpu();  // acquire: the other CTAs' partials
+            const int slab = pend_slab_s[i], ncontrib = pend_nc_s[i];
+            const int col0 = slab * kSlabCols;
+            const int ncols = min(kSlabCols, N - col0);
+            const float* sp = p.ws_partial + (size_t)slab * p.max_contrib * (NW * p.M * kSlabCols);
+            if (tid < ncols) {
+                for (int m = 0; m < p.M; ++m) {
+                    float a = 0.f, b = 0.f;
+                    // fixed summation order (deterministic); loads are issued in batches of 8 so that the L2 round trips overlap
+#pragma unroll 1
+                    for (int c0 = 0; c0 < ncontrib; c0 += 8) {
+                        float va[8], vb[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int c = min(c0 + j, ncontrib - 1);
                             const float* pc = sp + (size_t)c * (NW * p.M * kSlabCols);
-                            a += ld_cg(pc + (size_t)m * kSlabCols + tid);
-                            if constexpr (DUAL) b += ld_cg(pc + (size_t)(p.M + m) * kSlabCols + tid);
+                            va[j] = ld_cg(pc + (size_t)m * kSlabCols + tid);
+                            if constexpr (DUAL) vb[j] = ld_cg(pc + (size_t)(p.M + m) * kSlabCols + tid);
                         }
-                        p.out[(size_t)m * p.ldo + col0 + tid] = epilogue<DUAL>(p, a, b, m, col0 + tid);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            if (c0 + j < ncontrib) {
+                                a += va[j];
+                                if constexpr (DUAL) b += vb[j];
+                            }
+                        }
                     }
+                    p.out[(size_t)m * p.ldo + col0 + tid] = epilogue<DUAL>(p, a, b, m, col0 + tid);
                 }
             }
         }
-        u += nsteps;
-        TRACE(6);
     }
+    TRACE(6);
 }
-
-
 
 inline bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
 
@@ -478,8 +549,9 @@ bool skinny_supported(const QLinearArgs& a) {
     if (a.dual && (!aligned_to(a.w2.qweight, 16) || !aligned_to(a.w2.scales, 8))) return false;
     if (a.norm_w != nullptr && !aligned_to(a.norm_w, 16)) return false;
     const SkinnyPlan pl = plan_skinny(a.M, w.K, w.N);
-    const size_t smem = (size_t)a.M * (pl.seg_steps * 32 + 8) * sizeof(__half);
-    return smem <= 96 * 1024;
+    if (pl.total_units * (2LL * kNumSMs + 1) >= (1LL << 31)) return false;  // 32-bit unit arithmetic in the kernel
+    const size_t smem = (size_t)kWarps * kRingBytesPerWarp + (size_t)a.M * (pl.seg_steps * 32 + 32) * sizeof(__half);
+    return smem <= 110 * 1024;  // two CTAs per SM
 }
 
 cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl) {
@@ -514,7 +586,7 @@ cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl) {
     int pitch = pl.seg_steps * 32;
     if ((pitch / 32) % 2 == 0) pitch += 32;
     p.xs_pitch = pitch;
-    const size_t smem = (size_t)a.M * pitch * sizeof(__half);
+    const size_t smem = (size_t)kWarps * kRingBytesPerWarp + (size_t)a.M * pitch * sizeof(__half);
 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(pl.grid);
@@ -525,12 +597,15 @@ cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = (pdl && getenv("GPTQ_NO_PDL") == nullptr) ? 1 : 0;
+    cudaError_t e;
     if (a.dual) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(qmatvec_int4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        e = cudaFuncSetAttribute(qmatvec_int4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+        if (e != cudaSuccess) return e;
         return cudaLaunchKernelEx(&cfg, qmatvec_int4_kernel<true>, p);
     }
-    if (smem > 48 * 1024) cudaFuncSetAttribute(qmatvec_int4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(qmatvec_int4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+    if (e != cudaSuccess) return e;
     return cudaLaunchKernelEx(&cfg, qmatvec_int4_kernel<false>, p);
 }
 
