@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const __half* __restrict__
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct ScratchLayout {
-    size_t x, qkv, attn, h, xn, tmp, part, ws, total;
+    size_t x, qkv, attn, h, xn, tmp, part, ws, mega, total;
     size_t ws_bytes;
     int nsplit;
 };
@@ -347,6 +347,7 @@ ScratchLayout scratch_layout(const gptq_llama_model& m, int batch, int max_seq) 
     ws = max(ws, skinny_workspace_bytes(batch, m.intermediate, m.hidden, false));
     L.ws_bytes = ws;
     L.ws = take(ws);
+    L.mega = take(mega_scratch_bytes(m, max_seq));
     L.total = off;
     return L;
 }
@@ -395,6 +396,24 @@ extern "C" size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int ba
     return scratch_layout(*model, batch, max_seq).total;
 }
 
+extern "C" int gptq_llama_decode_launches(const gptq_llama_model* model, const gptq_llama_state* st) {
+    if (model == nullptr || st == nullptr || model->layers == nullptr) return GPTQ_ERR_NULL;
+    if (mega_supported(*model, *st)) return 1;
+    int n = 1 + 2 + (st->next_tokens != nullptr ? 1 : 0) - 1;  // embed + lm_head (+ argmax)
+    n = 1 + 1 + (st->next_tokens != nullptr ? 1 : 0);
+    for (int l = 0; l < model->n_layers; ++l) {
+        const gptq_llama_layer& ly = model->layers[l];
+        const gptq_qweight* ws[4] = {&ly.qkv, &ly.o, &ly.gate, &ly.down};
+        const int extra_norm[4] = {1, 0, 1, 0}, extra_res[4] = {0, 1, 0, 1};
+        n += 2;  // attention + combine
+        for (int i = 0; i < 4; ++i) {
+            const bool fast = ws[i]->bits == 4 && ws[i]->groupsize > 0 && ws[i]->groupsize % 32 == 0 && st->batch <= 8;
+            n += 1 + (fast ? 0 : extra_norm[i] + extra_res[i]);
+        }
+    }
+    return n;
+}
+
 extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_llama_state* st, gptq_stream_t stream_) {
     if (model == nullptr || st == nullptr) return GPTQ_ERR_NULL;
     const gptq_llama_model& m = *model;
@@ -417,6 +436,7 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     uint8_t* sc = reinterpret_cast<uint8_t*>(st->scratch);
+    if (mega_supported(m, *st)) return launch_decode_mega(m, *st, sc + L.mega, stream) == cudaSuccess ? GPTQ_OK : GPTQ_ERR_CUDA;
     __half* x = reinterpret_cast<__half*>(sc + L.x);
     __half* qkv = reinterpret_cast<__half*>(sc + L.qkv);
     __half* attn = reinterpret_cast<__half*>(sc + L.attn);

@@ -68,6 +68,7 @@ SIGNATURES = {
     'gptq_dequant': (c_int, [_QW, c_void_p, c_int64, c_void_p]),
     'gptq_llama_scratch_bytes': (c_size_t, [ctypes.POINTER(LlamaModel), c_int, c_int]),
     'gptq_llama_decode_step': (c_int, [ctypes.POINTER(LlamaModel), ctypes.POINTER(LlamaState), c_void_p]),
+    'gptq_llama_decode_launches': (c_int, [ctypes.POINTER(LlamaModel), ctypes.POINTER(LlamaState)]),
 }
 
 # gptq_status (include/gptq_b200.h)

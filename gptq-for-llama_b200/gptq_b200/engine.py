@@ -22,7 +22,8 @@ LLAMA_SHAPES = {  # hidden, intermediate, layers, heads
     '13b': (5120, 13824, 40, 40),
     '33b': (6656, 17920, 60, 52),
     '65b': (8192, 22016, 80, 64),
-    'tiny': (256, 704, 2, 2),
+    'tiny': (256, 704, 2, 2),    # intermediate not a multiple of 256: exercises the kernel-chain engine
+    'tiny256': (256, 768, 2, 2),  # eligible for the persistent single-kernel path
 }
 
 
@@ -127,14 +128,8 @@ class LlamaDecoder:
             torch.cuda.synchronize()
 
     def launches_per_step(self) -> int:
-        """Kernels of ours launched per decoded token: embed + 6 per layer + lm_head + argmax (general path: more)."""
-        extra = 0
-        for ly in self.layers:
-            for name, has_norm, has_res in (('qkv', 1, 0), ('o', 0, 1), ('gate', 1, 0), ('down', 0, 1)):
-                w = ly[name]
-                if not (w.bits == 4 and w.hint > 0 and w.hint % 32 == 0):
-                    extra += has_norm + has_res
-        return 1 + 6 * len(self.layers) + 2 + extra
+        """Kernels of ours launched per decoded token (1 on the persistent single-kernel path)."""
+        return int(lib.gptq_llama_decode_launches(ctypes.byref(self.model), ctypes.byref(self.state)))
 
     def step(self, stream=None):
         """Run one decode step on the tokens/positions currently in device memory."""

@@ -153,6 +153,9 @@ typedef struct gptq_llama_state {
 
 size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int batch, int max_seq);
 int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_llama_state* state, gptq_stream_t stream);
+/* Number of kernels one gptq_llama_decode_step launches for this model/state: 1 when the persistent single-kernel
+ * path applies (batch 1, every layer int4 without act-order), else the per-operation kernel chain. */
+int gptq_llama_decode_launches(const gptq_llama_model* model, const gptq_llama_state* state);
 
 #ifdef __cplusplus
 }

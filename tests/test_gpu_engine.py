@@ -47,10 +47,14 @@ def _oracle_decode(dec, token_ids):
     return torch.stack(outs)
 
 
-@pytest.mark.parametrize('bits,act,use_graph', [(4, False, True), (4, False, False), (4, True, True), (8, False, True), (3, True, True)])
-def test_decode_steps_match_oracle(bits, act, use_graph):
+@pytest.mark.parametrize('size,bits,act,use_graph', [('tiny', 4, False, True), ('tiny', 4, False, False), ('tiny', 4, True, True), ('tiny', 8, False, True),
+                                                     ('tiny', 3, True, True), ('tiny256', 4, False, True), ('tiny256', 4, False, False)])
+def test_decode_steps_match_oracle(size, bits, act, use_graph):
     from gptq_b200 import engine
-    dec = engine.synthetic_llama('tiny', bits=bits, groupsize=64, act_order=act, vocab=512, seed=bits, max_seq=600, use_graph=use_graph)
+    dec = engine.synthetic_llama(size, bits=bits, groupsize=64, act_order=act, vocab=512, seed=bits, max_seq=600, use_graph=use_graph)
+    assert dec.launches_per_step() == (1 if (size == 'tiny256' and bits == 4 and not act) else dec.launches_per_step())
+    if size == 'tiny256':
+        assert dec.launches_per_step() == 1  # persistent single-kernel path
     gen = torch.Generator().manual_seed(0)
     toks = torch.randint(0, 512, (6, ), generator=gen).tolist()
     ref = _oracle_decode(dec, toks)
@@ -63,10 +67,11 @@ def test_decode_steps_match_oracle(bits, act, use_graph):
         assert int(dec.next_tokens[0]) == int(dec.logits[0].float().argmax())
 
 
-def test_long_context_attention_splits():
-    """Positions beyond one 256-key attention chunk: split-KV partials + combine against the oracle."""
+@pytest.mark.parametrize('size', ['tiny', 'tiny256'])
+def test_long_context_attention_splits(size):
+    """Positions beyond one attention chunk: split-KV partials + combine against the oracle (both engines)."""
     from gptq_b200 import engine
-    dec = engine.synthetic_llama('tiny', bits=4, groupsize=128, vocab=256, seed=1, max_seq=640)
+    dec = engine.synthetic_llama(size, bits=4, groupsize=128, vocab=256, seed=1, max_seq=640)
     toks = torch.randint(0, 256, (530, ), generator=torch.Generator().manual_seed(1)).tolist()
     ref = _oracle_decode(dec, toks)
     for pos, tok in enumerate(toks):
