@@ -34,12 +34,34 @@ using namespace int4;
 constexpr int kWarps = 8;
 constexpr int kThreads = 256;
 constexpr int kSlabCols = 256;
-constexpr int kRingBytesPerWarp = 8192;
-constexpr int kTile = 512;                          // one ring stage: 4 packed rows x 32 columns of one matrix
-constexpr int kStages = kRingBytesPerWarp / kTile;  // 16
+constexpr int kProducers = 2;                      // producer warps: tile i is fetched by producer i % kProducers
+constexpr int kBlock = kThreads + 32 * kProducers;  // 8 consumer warps + the producer warps
+constexpr int kRowPitch = 1024 + 32;   // smem pitch of a 1 KB weight row: +32 B makes the 4 rows of a k-step hit distinct bank groups
+constexpr int kTile = 4 * kRowPitch;   // one ring stage: 4 packed rows x 256 columns of one matrix (4 KB of weights)
+constexpr int kStages = 15;            // 15 x 4224 B = 63,360 B of weights in flight per CTA
 constexpr int kHD = 128;
 constexpr int kAttnChunk = 128;  // keys per attention work item
+constexpr int kRec = kHD + 4;     // floats per split-KV partial record: m, l, 2 pad, o[128] (keeps o 16-byte aligned)
 constexpr int kMaxLayers = 80;
+
+#ifdef GPTQ_TRACE
+}  // namespace
+__device__ unsigned long long* g_mega_trace = nullptr;
+namespace {
+
+#define MTRACE(id)                                                                                                       \
+    do {                                                                                                                 \
+        if (g_mega_trace != nullptr && threadIdx.x == 0 && (id) < 64) {                                                   \
+            unsigned long long t_;                                                                                       \
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                                        \
+            g_mega_trace[blockIdx.x * 64 + (id)] = t_;                                                                   \
+        }                                                                                                                \
+    } while (0)
+#else
+#define MTRACE(id) \
+    do {           \
+    } while (0)
+#endif
 
 struct MatDesc {
     const uint32_t* qw;
@@ -73,7 +95,7 @@ struct MegaParams {
     float* acc_d;      // [H]
     float* part;       // [heads][nsplit][130]
     float* rope_cs;    // [128]: cos[64], sin[64] of this step's position
-    unsigned* bar;     // [0] arrival count, [1] generation
+    unsigned long long* bar;  // monotonic arrival counter of the grid barrier
     LayerDesc layers[kMaxLayers];
 };
 
@@ -98,84 +120,86 @@ __device__ __forceinline__ MatOp mat_op(const MegaParams& p, int idx) {
     return m;
 }
 
-// ---- weight producer: this lane's stream of 16-byte copies, running ahead across ops -------------------
-struct Producer {
-    const uint4* gp[2];
-    long long wrap;  // uint4 delta: next slab, back to packed row 0
-    int N;           // row advance per k-step in uint4 units (= N)
-    int nk, dual;
-    int left;       // k-steps of the current op not yet requested
-    int rows_left;  // ... until the slab ends
-    int next_op;    // index of the next matvec op to load from
-    int n_ops;
-    int phase;  // dual: 0 = gate tile next, 1 = up tile next
+// ---- pipeline state --------------------------------------------------------------------------------------
+// A dedicated producer warp streams 4 KB tiles (4 packed rows x 1 KB: whole DRAM-page-sized row segments, one
+// cp.async.bulk each) into a 15-stage ring shared by the CTA; the 8 consumer warps each read their 32-column
+// stripe of every tile.  full[s]: producer -> consumers (expect_tx 4096 B); empty[s]: 8 consumer warps -> producer.
+// The producer walks the matvec list of the whole token on its own, so it runs ahead across grid barriers.
+struct Pipe {
+    uint32_t ring;   // smem address of stage 0
+    uint32_t full;   // smem address of full[0]  (8 B each; empty[s] sits kStages * 8 bytes after full[s])
+    uint32_t empty;  // smem address of empty[0]
+    // consumer cursors (per thread): stages are consumed in strict rotation, so one parity bit per round suffices
+    uint32_t tile;    // smem address of this lane's 16 B in the current stage
+    uint32_t bar;     // smem address of full[current stage]
+    uint32_t parity;  // expected parity of the current round
+    int left;         // stages until the ring wraps
 };
 
-__device__ __forceinline__ void producer_open(Producer& pr, const MegaParams& p, int lane_t, int lane_g, int warp) {
-    // advance to the next op that has work for this CTA
-    while (pr.next_op < pr.n_ops) {
-        const MatOp m = mat_op(p, pr.next_op++);
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 consumer warps only
+
+__device__ void producer_loop(const MegaParams& p, uint32_t ring, uint32_t full, uint32_t empty, int pw) {
+    int stage = 0, use = 0, mine = 0;  // ring position / use count of the next tile; mine: tiles until this producer's turn
+    mine = pw;
+    const int n_ops = p.n_layers * 4;
+#pragma unroll 1
+    for (int op = 0; op < n_ops; ++op) {
+        const MatOp m = mat_op(p, op);
         const unsigned nk = m.K / 32, U = (unsigned)(m.N / kSlabCols) * nk, nb = gridDim.x;
         const int u0 = (int)((blockIdx.x * U) / nb), u1 = (int)(((blockIdx.x + 1) * U) / nb);
         if (u1 <= u0) continue;
-        const int slab = u0 / nk, ks = u0 - slab * nk;
-        const size_t off = (size_t)(ks * 4 + lane_t) * m.N + slab * kSlabCols + warp * 32 + 4 * lane_g;
-        pr.gp[0] = reinterpret_cast<const uint4*>(m.qw[0] + off);
-        pr.gp[1] = m.qw[1] ? reinterpret_cast<const uint4*>(m.qw[1] + off) : nullptr;
-        pr.N = m.N;
-        pr.nk = nk;
-        pr.dual = m.ntiles_per_step == 2;
-        pr.wrap = (long long)(kSlabCols / 4) - (long long)nk * m.N;
-        pr.left = u1 - u0;
-        pr.rows_left = nk - ks;
-        pr.phase = 0;
-        return;
-    }
-    pr.left = 0;
-}
-
-// request one tile into ring slot `dst` (or nothing once all ops are exhausted); always commits a group
-__device__ __forceinline__ void produce(Producer& pr, const MegaParams& p, uint32_t dst, int lane_t, int lane_g, int warp) {
-    if (pr.left == 0 && pr.next_op < pr.n_ops) producer_open(pr, p, lane_t, lane_g, warp);
-    if (pr.left > 0) {
-        cp_async16(dst, pr.gp[pr.phase]);
-        if (pr.dual && pr.phase == 0) {
-            pr.phase = 1;
-        } else {
-            pr.phase = 0;
-            pr.gp[0] += pr.N;
-            if (pr.dual) pr.gp[1] += pr.N;
-            --pr.left;
-            if (--pr.rows_left == 0) {
-                pr.gp[0] += pr.wrap;
-                if (pr.dual) pr.gp[1] += pr.wrap;
-                pr.rows_left = pr.nk;
+        const int slab0 = u0 / nk;
+        int ks = u0 - slab0 * nk;
+        const size_t row_bytes = (size_t)m.N * 4;
+        const uint8_t* src[2];
+        src[0] = reinterpret_cast<const uint8_t*>(m.qw[0]) + (size_t)(ks * 4) * row_bytes + (size_t)slab0 * (kSlabCols * 4);
+        src[1] = m.qw[1] ? reinterpret_cast<const uint8_t*>(m.qw[1]) + (size_t)(ks * 4) * row_bytes + (size_t)slab0 * (kSlabCols * 4) : nullptr;
+        const long long wrap = (long long)(kSlabCols * 4) - (long long)nk * 4 * (long long)row_bytes;  // next slab, back to packed row 0
+#pragma unroll 1
+        for (int u = u0; u < u1; ++u) {
+#pragma unroll 1
+            for (int w = 0; w < m.ntiles_per_step; ++w) {
+                if (mine == 0) {
+                    if (use > 0) mbar_wait(empty + stage * 8, (use - 1) & 1u);  // consumers released the previous use of this stage
+                    const uint32_t bar = full + stage * 8;
+                    const uint32_t dst = ring + stage * kTile;
+                    mbar_expect_tx(bar, 4096);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) bulk_copy_g2s(dst + r * kRowPitch, src[w] + r * row_bytes, 1024, bar);
+                    mine = kProducers;
+                }
+                --mine;
+                if (++stage == kStages) {
+                    stage = 0;
+                    ++use;
+                }
+            }
+            src[0] += 4 * row_bytes;
+            if (src[1]) src[1] += 4 * row_bytes;
+            if (++ks == (int)nk) {
+                ks = 0;
+                src[0] += wrap;
+                if (src[1]) src[1] += wrap;
             }
         }
     }
-    cp_async_commit();
 }
 
-// ---- grid barrier: count + generation (sense-reversing), release/acquire at gpu scope -------------------
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& gen) {
-    __syncthreads();
+// ---- grid barrier: one monotonic 64-bit arrival counter (never reset: every launch adds a multiple of gridDim.x) ----
+// arrive = red.release (fire and forget), wait = poll the same word with ld.acquire until it reaches this barrier's
+// target: about 1.5 L2 round trips.  `target` lives in thread 0 of each CTA.
+__device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long& target) {
+    cta_sync();
     if (threadIdx.x == 0) {
-        fence_acq_rel_gpu();
-        const unsigned old = atomicAdd(bar, 1u);
-        if (old == gridDim.x - 1) {
-            bar[0] = 0;
-            fence_acq_rel_gpu();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            unsigned v;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + 1));
-            } while (v == gen);
-        }
-        fence_acq_rel_gpu();
+        target += gridDim.x;
+        asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(bar) : "memory");
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
+        } while (v < target);
+        fence_acq_rel_gpu();  // also drops this SM's stale L1 lines of data other CTAs have rewritten
     }
-    ++gen;
-    __syncthreads();
+    cta_sync();
 }
 
 __device__ __forceinline__ void zero_slice(float* buf, int n) {
@@ -187,9 +211,9 @@ __device__ __forceinline__ void zero_slice(float* buf, int n) {
 
 __device__ __forceinline__ float block_sum(float v, float* red_s) {
     v = warp_sum(v);
-    __syncthreads();
+    cta_sync();
     if ((threadIdx.x & 31) == 0) red_s[threadIdx.x >> 5] = v;
-    __syncthreads();
+    cta_sync();
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) t += red_s[w];
@@ -254,7 +278,7 @@ enum XMode { X_FULL = 0, X_ATTN = 1, X_SWIGLU = 2 };
 // One matvec op for this CTA: consume the tiles of its unit range from the ring, RED the results.
 // xs holds either the full K row (X_FULL, staged by stage_norm before the call) or is (re)staged per segment here.
 template <bool DUAL, int XMODE>
-__device__ void run_matvec(const MegaParams& p, Producer& pr, uint32_t& slot, uint32_t ring_lo, uint32_t ring_hi, const MatDesc& w0, const MatDesc& w1, int K, int N,
+__device__ void run_matvec(const MegaParams& p, Pipe& pipe, const MatDesc& w0, const MatDesc& w1, int K, int N,
                            float* out0, float* out1, __half* xs) {
     constexpr int NW = DUAL ? 2 : 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -263,6 +287,10 @@ __device__ void run_matvec(const MegaParams& p, Producer& pr, uint32_t& slot, ui
     const int gs_steps = p.groupsize >> 5;
     const MatDesc* wd[2] = {&w0, &w1};
 
+#ifdef GPTQ_TRACE
+    long long wait_cycles = 0;
+    const long long tm0 = clock64();
+#endif
     int u = u_begin;
 #pragma unroll 1
     while (u < u_end) {
@@ -293,40 +321,41 @@ __device__ void run_matvec(const MegaParams& p, Producer& pr, uint32_t& slot, ui
             xaddr = smem_u32(xs) + (ks0 * 32 + t * 8) * 2;
         } else {
             // stage this segment's k-range [ks0*32, (ks0+nsteps)*32) of the op input
-            __syncthreads();  // previous readers of xs are done
+            cta_sync();  // previous readers of xs are done
             const int kbeg = ks0 * 32;
-            for (int c = tid; c < nsteps * 4; c += kThreads) {
-                const int k = kbeg + c * 8;
-                uint32_t o[4];
-                if constexpr (XMODE == X_SWIGLU) {  // h = fp16(silu(acc_gate) * acc_up)  (quant/fused_mlp.py:163-165)
+            if constexpr (XMODE == X_SWIGLU) {  // h = fp16(silu(acc_gate) * acc_up)  (quant/fused_mlp.py:163-165)
+                for (int c = tid; c < nsteps * 4; c += kThreads) {
+                    const int k = kbeg + c * 8;
+                    uint32_t o[4];
                     const float4 g0 = *reinterpret_cast<const float4*>(p.acc_g + k), g1 = *reinterpret_cast<const float4*>(p.acc_g + k + 4);
                     const float4 u0 = *reinterpret_cast<const float4*>(p.acc_u + k), u1 = *reinterpret_cast<const float4*>(p.acc_u + k + 4);
                     o[0] = h2_as_u32(__floats2half2_rn(swiglu(g0.x, u0.x), swiglu(g0.y, u0.y)));
                     o[1] = h2_as_u32(__floats2half2_rn(swiglu(g0.z, u0.z), swiglu(g0.w, u0.w)));
                     o[2] = h2_as_u32(__floats2half2_rn(swiglu(g1.x, u1.x), swiglu(g1.y, u1.y)));
                     o[3] = h2_as_u32(__floats2half2_rn(swiglu(g1.z, u1.z), swiglu(g1.w, u1.w)));
-                } else {  // attention output: combine the split-KV partials of head k / 128
+                    store_perm8(xs + c * 8, o[0], o[1], o[2], o[3]);
+                }
+            } else {  // attention output: one thread per feature combines the split-KV partials of its head (coalesced over d)
+                const int nvalid = min(p.nsplit, p.positions[0] / kAttnChunk + 1);
+                for (int e = tid; e < nsteps * 32; e += kThreads) {
+                    const int k = kbeg + e;
                     const int head = k / kHD, d = k - head * kHD;
-                    const int nvalid = min(p.nsplit, p.positions[0] / kAttnChunk + 1);
-                    const float* src = p.part + (size_t)head * p.nsplit * (kHD + 2);
+                    const float* src = p.part + (size_t)head * p.nsplit * kRec;
                     float M = -INFINITY;
-                    for (int s = 0; s < nvalid; ++s) M = fmaxf(M, src[(size_t)s * (kHD + 2)]);
-                    float L = 0.f, O[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) O[j] = 0.f;
-                    for (int s = 0; s < nvalid; ++s) {
-                        const float* ps = src + (size_t)s * (kHD + 2);
+                    for (int sI = 0; sI < nvalid; ++sI) M = fmaxf(M, src[(size_t)sI * kRec]);
+                    float L = 0.f, O = 0.f;
+#pragma unroll 4
+                    for (int sI = 0; sI < nvalid; ++sI) {
+                        const float* ps = src + (size_t)sI * kRec;
                         const float wgt = expf(ps[0] - M);
                         L = fmaf(ps[1], wgt, L);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) O[j] = fmaf(ps[2 + d + j], wgt, O[j]);
+                        O = fmaf(ps[4 + d], wgt, O);
                     }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) o[j] = h2_as_u32(__floats2half2_rn(O[2 * j] / L, O[2 * j + 1] / L));
+                    const int j8 = e & 7;
+                    xs[(e & ~7) + ((j8 & 3) << 1) + (j8 >> 2)] = __float2half_rn(O / L);  // k-permuted position inside the run of 8
                 }
-                store_perm8(xs + c * 8, o[0], o[1], o[2], o[3]);
             }
-            __syncthreads();
+            cta_sync();
             xaddr = smem_u32(xs) + (t * 8) * 2;
         }
 
@@ -350,6 +379,30 @@ __device__ void run_matvec(const MegaParams& p, Producer& pr, uint32_t& slot, ui
             }
         }
 
+        // software pipeline: the NEXT tile's wait + shared-memory load are issued before the current tile's math, so the
+        // ~120 cycles of mbarrier-probe + LDS latency overlap with ~80 instructions of dequant/MMA
+        auto fetch = [&](uint4& q, uint32_t& bar_of_q) {
+#ifdef GPTQ_TRACE
+            const long long tw0 = clock64();
+#endif
+            mbar_wait(pipe.bar, pipe.parity);  // the tile has landed
+#ifdef GPTQ_TRACE
+            wait_cycles += clock64() - tw0;
+#endif
+            q = lds128(pipe.tile);
+            bar_of_q = pipe.bar;
+            pipe.tile += kTile;
+            pipe.bar += 8;
+            if (--pipe.left == 0) {  // ring wrap: next round, other parity
+                pipe.left = kStages;
+                pipe.tile -= kStages * kTile;
+                pipe.bar -= kStages * 8;
+                pipe.parity ^= 1u;
+            }
+        };
+        uint4 q_cur;
+        uint32_t bar_cur;
+        fetch(q_cur, bar_cur);
 #pragma unroll 1
         for (int step = 0; step < nsteps; ++step) {
             if (steps_left_in_grp == 0) {
@@ -370,20 +423,22 @@ __device__ void run_matvec(const MegaParams& p, Producer& pr, uint32_t& slot, ui
             xaddr += 64;
 #pragma unroll
             for (int w = 0; w < NW; ++w) {
-                cp_async_wait<kStages - 1>();  // the oldest tile of this lane has landed
-                const uint4 q = lds128(slot);
+                uint4 q_next = q_cur;
+                uint32_t bar_next = bar_cur;
+                if (w + 1 < NW || step + 1 < nsteps) fetch(q_next, bar_next);  // prefetch the following tile of this segment
                 uint32_t wf[4][4];
-                dequant8<0>(q.x, gc[w].za01, gc[w].zb01, gc[w].s01, wf[0]);
-                dequant8<1>(q.y, gc[w].za01, gc[w].zb01, gc[w].s01, wf[1]);
-                dequant8<0>(q.z, gc[w].za23, gc[w].zb23, gc[w].s23, wf[2]);
-                dequant8<1>(q.w, gc[w].za23, gc[w].zb23, gc[w].s23, wf[3]);
+                dequant8<0>(q_cur.x, gc[w].za01, gc[w].zb01, gc[w].s01, wf[0]);
+                dequant8<1>(q_cur.y, gc[w].za01, gc[w].zb01, gc[w].s01, wf[1]);
+                dequant8<0>(q_cur.z, gc[w].za23, gc[w].zb23, gc[w].s23, wf[2]);
+                dequant8<1>(q_cur.w, gc[w].za23, gc[w].zb23, gc[w].s23, wf[3]);
                 mma_16816(acc[w][0], wf[0][0], wf[1][0], wf[0][1], wf[1][1], xf.x, xf.y);
                 mma_16816(acc[w][0], wf[0][2], wf[1][2], wf[0][3], wf[1][3], xf.z, xf.w);
                 mma_16816(acc[w][1], wf[2][0], wf[3][0], wf[2][1], wf[3][1], xf.x, xf.y);
                 mma_16816(acc[w][1], wf[2][2], wf[3][2], wf[2][3], wf[3][3], xf.z, xf.w);
-                produce(pr, p, slot, t, g, warp);  // refill the slot just consumed (kStages tiles ahead, possibly of a later op)
-                slot += kTile;
-                if (slot == ring_hi) slot = ring_lo;
+                __syncwarp();  // every lane has consumed the registers it read from the current tile's stage
+                if (lane == 0) mbar_arrive(bar_cur + kStages * 8);  // empty[stage]
+                q_cur = q_next;
+                bar_cur = bar_next;
             }
         }
 
@@ -399,6 +454,14 @@ __device__ void run_matvec(const MegaParams& p, Producer& pr, uint32_t& slot, ui
         }
         u += nsteps;
     }
+#ifdef GPTQ_TRACE
+    if (g_mega_trace != nullptr && threadIdx.x == 0) {
+        const int base = DUAL ? 40 : (XMODE == X_FULL ? 44 : (XMODE == X_ATTN ? 48 : 52));
+        g_mega_trace[blockIdx.x * 64 + base] = (unsigned long long)(clock64() - tm0);
+        g_mega_trace[blockIdx.x * 64 + base + 1] = (unsigned long long)wait_cycles;
+        g_mega_trace[blockIdx.x * 64 + base + 2] = (unsigned long long)(u_end - u_begin);
+    }
+#endif
 }
 
 // Attention work items (head, split): RoPE(q,k) from this step's cos/sin, KV append, partial softmax(qK^T)V.
@@ -421,7 +484,7 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
         const int c1 = min(c0 + kAttnChunk, T);
         __half* kc = kc_base + (size_t)head * p.max_seq * kHD;
         __half* vc = vc_base + (size_t)head * p.max_seq * kHD;
-        __syncthreads();  // smem reuse across items
+        cta_sync();  // smem reuse across items
         if (tid < kHD) {
             const int i = tid & 63;
             const bool hi = tid >= 64;
@@ -439,28 +502,40 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
                 vc[(size_t)pos * kHD + tid] = __float2half_rn(av[tid]);
             }
         }
-        __syncthreads();
+        cta_sync();
         const int grp = tid >> 3, j = tid & 7;  // 32 groups of 8 lanes; lane j owns dims [16j, 16j+16)
+        constexpr int ITER = kAttnChunk / 32;
+        // all K and V rows of this lane are requested up front (clamped indices): two DRAM round trips per item, not one per key
+        uint4 kreg[ITER][2], vreg[ITER][2];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int tk = min(c0 + grp + it * 32, c1 - 1);
+            const uint4* kp = reinterpret_cast<const uint4*>(kc + (size_t)tk * kHD + 16 * j);
+            kreg[it][0] = kp[0];
+            kreg[it][1] = kp[1];
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+            const int tk = min(c0 + grp + it * 32, c1 - 1);
+            const uint4* vp = reinterpret_cast<const uint4*>(vc + (size_t)tk * kHD + 16 * j);
+            vreg[it][0] = vp[0];
+            vreg[it][1] = vp[1];
+        }
         float qr[16];
 #pragma unroll
         for (int d = 0; d < 16; ++d) qr[d] = q_s[16 * j + d];
-        constexpr int ITER = kAttnChunk / 32;
         float sc[ITER];
         float mloc = -INFINITY;
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int tk = c0 + grp + it * 32;
+            const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w, kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
             float s = 0.f;
-            if (tk < c1) {
-                const uint4* kp = reinterpret_cast<const uint4*>(kc + (size_t)tk * kHD + 16 * j);
-                const uint4 a = kp[0], b = kp[1];
-                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float2 f = __half22float2(u32_as_h2(w[e]));
-                    s = fmaf(qr[2 * e], f.x, s);
-                    s = fmaf(qr[2 * e + 1], f.y, s);
-                }
+            for (int e = 0; e < 8; ++e) {
+                const float2 f = __half22float2(u32_as_h2(w[e]));
+                s = fmaf(qr[2 * e], f.x, s);
+                s = fmaf(qr[2 * e + 1], f.y, s);
             }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
@@ -475,18 +550,14 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int tk = c0 + grp + it * 32;
-            if (tk < c1) {
-                const float pw = expf(sc[it] - mloc);
-                lloc += pw;
-                const uint4* vp = reinterpret_cast<const uint4*>(vc + (size_t)tk * kHD + 16 * j);
-                const uint4 a = vp[0], b = vp[1];
-                const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            const float pw = (tk < c1) ? expf(sc[it] - mloc) : 0.f;
+            lloc += pw;
+            const uint32_t w[8] = {vreg[it][0].x, vreg[it][0].y, vreg[it][0].z, vreg[it][0].w, vreg[it][1].x, vreg[it][1].y, vreg[it][1].z, vreg[it][1].w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float2 f = __half22float2(u32_as_h2(w[e]));
-                    o[2 * e] = fmaf(pw, f.x, o[2 * e]);
-                    o[2 * e + 1] = fmaf(pw, f.y, o[2 * e + 1]);
-                }
+            for (int e = 0; e < 8; ++e) {
+                const float2 f = __half22float2(u32_as_h2(w[e]));
+                o[2 * e] = fmaf(pw, f.x, o[2 * e]);
+                o[2 * e + 1] = fmaf(pw, f.y, o[2 * e + 1]);
             }
         }
         if (j == 0) {
@@ -495,7 +566,7 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
         }
 #pragma unroll
         for (int d = 0; d < 16; ++d) red_o[grp * 132 + 16 * j + d] = o[d];
-        __syncthreads();
+        cta_sync();
         if (tid < kHD) {
             float M = -INFINITY;
 #pragma unroll 8
@@ -507,8 +578,8 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
                 L = fmaf(red_l[gI], wgt, L);
                 O = fmaf(red_o[gI * 132 + tid], wgt, O);
             }
-            float* dst = p.part + ((size_t)head * p.nsplit + split) * (kHD + 2);
-            dst[2 + tid] = O;
+            float* dst = p.part + ((size_t)head * p.nsplit + split) * kRec;
+            dst[4 + tid] = O;
             if (tid == 0) {
                 dst[0] = M;
                 dst[1] = L;
@@ -517,25 +588,42 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) llama_decode_mega_kernel(const __grid_constant__ MegaParams p) {
+__global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ float red_s[kWarps];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    // smem: [rings 64 KB][xs: max(H, I-segment) halves][tmp: H halves / attention scratch]
-    __half* xs = reinterpret_cast<__half*>(smem_raw + kWarps * kRingBytesPerWarp);
+    __shared__ __align__(8) unsigned long long bars_s[2 * kStages];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // smem: [ring: 15 x 4224 B][xs: H halves][tmp: H halves / attention scratch]
+    constexpr int kRingBytes = ((kStages * kTile + 127) / 128) * 128;
+    __half* xs = reinterpret_cast<__half*>(smem_raw + kRingBytes);
     __half* tmp = xs + p.H;
-    const uint32_t ring_lo = smem_u32(smem_raw) + warp * kRingBytesPerWarp + lane * 16;
-    const uint32_t ring_hi = ring_lo + kRingBytesPerWarp;
-    uint32_t slot = ring_lo;
-    unsigned gen;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(p.bar + 1));
-
-    Producer pr{};
-    pr.n_ops = p.n_layers * 4;
-    pr.next_op = 0;
-    pr.left = 0;
-#pragma unroll 1
-    for (int s = 0; s < kStages; ++s) produce(pr, p, ring_lo + s * kTile, t, g, warp);
+    Pipe pipe;
+    pipe.ring = smem_u32(smem_raw);
+    pipe.full = smem_u32(&bars_s[0]);
+    pipe.empty = smem_u32(&bars_s[kStages]);
+    pipe.tile = pipe.ring + (lane & 3) * kRowPitch + (warp & 7) * 128 + (lane >> 2) * 16;  // row t of the tile, this lane's 4 columns
+    pipe.bar = pipe.full;
+    pipe.parity = 0;
+    pipe.left = kStages;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(pipe.full + s * 8, 1);
+            mbar_init(pipe.empty + s * 8, kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();  // the only block-wide barrier: after it the producer warp and the consumers never meet again
+    if (warp >= kWarps) {
+        if (lane == 0) producer_loop(p, pipe.ring, pipe.full, pipe.empty, warp - kWarps);
+        return;
+    }
+    unsigned long long gen;  // barrier target (meaningful in thread 0): the counter value when this launch began
+    {
+        unsigned long long v;
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar) : "memory");
+        gen = v - (v % gridDim.x);  // CTAs that already arrived at the first barrier have added < gridDim.x
+    }
 
     // this step's RoPE angles (quant/fused_attn.py:43,91): freq_i = exp(i * inv_base) * pos
     if (blockIdx.x == 0 && tid < 64) {
@@ -552,30 +640,42 @@ __global__ void __launch_bounds__(kThreads, 2) llama_decode_mega_kernel(const __
     for (int l = 0; l < p.n_layers; ++l) {
         const LayerDesc& L = p.layers[l];
         // ---- Q ----
+        MTRACE(l * 12 + 0);
         stage_norm(p, resid_src, resid_acc, L.input_norm, p.resid[cur ^ 1], xs, tmp, red_s);
+        MTRACE(l * 12 + 1);
         cur ^= 1;
         zero_slice(p.acc_g, p.I);  // last read by the previous layer's D
         zero_slice(p.acc_u, p.I);
-        __syncthreads();
-        run_matvec<false, X_FULL>(p, pr, slot, ring_lo, ring_hi, L.qkv, L.qkv, p.H, 3 * p.H, p.acc_qkv, nullptr, xs);
+        cta_sync();
+        run_matvec<false, X_FULL>(p, pipe, L.qkv, L.qkv, p.H, 3 * p.H, p.acc_qkv, nullptr, xs);
+        MTRACE(l * 12 + 2);
         grid_barrier(p.bar, gen);
+        MTRACE(l * 12 + 3);
         // ---- A ----
         zero_slice(p.acc_d, p.H);  // last read by this layer's Q
         run_attention(p, l, reinterpret_cast<float*>(tmp));
+        MTRACE(l * 12 + 4);
         grid_barrier(p.bar, gen);
+        MTRACE(l * 12 + 5);
         // ---- O ----
         zero_slice(p.acc_qkv, 3 * p.H);
-        run_matvec<false, X_ATTN>(p, pr, slot, ring_lo, ring_hi, L.o, L.o, p.H, p.H, p.acc_o, nullptr, xs);
+        run_matvec<false, X_ATTN>(p, pipe, L.o, L.o, p.H, p.H, p.acc_o, nullptr, xs);
+        MTRACE(l * 12 + 6);
         grid_barrier(p.bar, gen);
+        MTRACE(l * 12 + 7);
         // ---- G ----
         stage_norm(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, tmp, red_s);
         cur ^= 1;
-        __syncthreads();
-        run_matvec<true, X_FULL>(p, pr, slot, ring_lo, ring_hi, L.gate, L.up, p.H, p.I, p.acc_g, p.acc_u, xs);
+        cta_sync();
+        MTRACE(l * 12 + 8);
+        run_matvec<true, X_FULL>(p, pipe, L.gate, L.up, p.H, p.I, p.acc_g, p.acc_u, xs);
+        MTRACE(l * 12 + 9);
         grid_barrier(p.bar, gen);
         // ---- D ----
         zero_slice(p.acc_o, p.H);
-        run_matvec<false, X_SWIGLU>(p, pr, slot, ring_lo, ring_hi, L.down, L.down, p.I, p.H, p.acc_d, nullptr, xs);
+        MTRACE(l * 12 + 10);
+        run_matvec<false, X_SWIGLU>(p, pipe, L.down, L.down, p.I, p.H, p.acc_d, nullptr, xs);
+        MTRACE(l * 12 + 11);
         grid_barrier(p.bar, gen);
         resid_src = p.resid[cur];
         resid_acc = p.acc_d;
@@ -584,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 2) llama_decode_mega_kernel(const __
     stage_norm(p, resid_src, resid_acc, p.final_norm, nullptr, xs, tmp, red_s);
     zero_slice(p.acc_g, p.I);
     zero_slice(p.acc_u, p.I);
-    __syncthreads();
+    cta_sync();
     {
         const int chunks = p.H / 8;
 #pragma unroll 1
@@ -638,7 +738,7 @@ __global__ void __launch_bounds__(kThreads, 2) llama_decode_mega_kernel(const __
             sv[warp] = best;
             si[warp] = idx;
         }
-        __syncthreads();
+        cta_sync();
         if (tid == 0) {
             for (int w = 1; w < kWarps; ++w)
                 if (sv[w] > best || (sv[w] == best && si[w] < idx)) {
@@ -675,7 +775,7 @@ bool mega_supported(const gptq_llama_model& m, const gptq_llama_state& st) {
 size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq) {
     const int nsplit = ceil_div(max_seq, kAttnChunk);
     return al256((size_t)m.hidden * 2) * 2 + al256((size_t)3 * m.hidden * 4) + al256((size_t)m.hidden * 4) * 2 + al256((size_t)m.intermediate * 4) * 2 +
-           al256((size_t)m.n_heads * nsplit * (kHD + 2) * 4) + al256(128 * 4) + 256;
+           al256((size_t)m.n_heads * nsplit * kRec * 4) + al256(128 * 4) + 256;
 }
 
 cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream) {
@@ -711,9 +811,9 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     p.acc_d = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
     p.acc_g = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
     p.acc_u = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
-    p.part = reinterpret_cast<float*>(take((size_t)m.n_heads * p.nsplit * (kHD + 2) * 4));
+    p.part = reinterpret_cast<float*>(take((size_t)m.n_heads * p.nsplit * kRec * 4));
     p.rope_cs = reinterpret_cast<float*>(take(128 * 4));
-    p.bar = reinterpret_cast<unsigned*>(take(256));
+    p.bar = reinterpret_cast<unsigned long long*>(take(256));
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         auto md = [](const gptq_qweight& w) {
@@ -734,7 +834,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     // smem: rings + xs (max(H, widest staged segment)) + tmp (H halves or the attention scratch)
     const size_t xs_halves = (size_t)m.hidden;  // segments of the down projection are far shorter than H (checked below)
     const size_t tmp_bytes = max((size_t)m.hidden * 2, (size_t)(192 + 32 * 132) * 4);
-    const size_t smem = (size_t)kWarps * kRingBytesPerWarp + xs_halves * 2 + tmp_bytes;
+    const size_t smem = (size_t)(((kStages * kTile + 127) / 128) * 128) + xs_halves * 2 + tmp_bytes;
     const int grid = 2 * kNumSMs;
     // the per-CTA k-segment of the down projection must fit in xs
     const long long seg_steps = ((long long)(m.hidden / kSlabCols) * (m.intermediate / 32) + grid - 1) / grid;
@@ -743,7 +843,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(kBlock);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -755,3 +855,10 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
 }
 
 }  // namespace gptq
+
+#ifdef GPTQ_TRACE
+extern "C" int gptq_debug_set_mega_trace(void* buf) {
+    unsigned long long* b = reinterpret_cast<unsigned long long*>(buf);
+    return (int)cudaMemcpyToSymbol(gptq::g_mega_trace, &b, sizeof(b));
+}
+#endif
