@@ -64,6 +64,7 @@ static int run_qlinear(const QLinearArgs& a) {
         if ((reinterpret_cast<uintptr_t>(a.workspace) & 255) != 0) return GPTQ_ERR_ALIGN;
         return cuda_status(launch_qlinear_skinny(a, false));
     }
+    if (gemm_tc_supported(a)) return cuda_status(launch_qlinear_gemm_tc(a));
     return cuda_status(launch_qlinear_generic(a));
 }
 

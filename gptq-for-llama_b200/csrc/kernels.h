@@ -40,6 +40,10 @@ size_t skinny_workspace_bytes(int M, int K, int N, bool dual);
 bool skinny_supported(const QLinearArgs& a);
 cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl);
 
+// qgemm_tcgen05.cu -- batched (prefill) int4 GEMM on tcgen05 tensor cores, M > 8
+bool gemm_tc_supported(const QLinearArgs& a);
+cudaError_t launch_qlinear_gemm_tc(const QLinearArgs& a);
+
 // decode_mega.cu -- persistent single-kernel decode step (batch 1, int4, no act-order)
 bool mega_supported(const gptq_llama_model& m, const gptq_llama_state& st);
 size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq);

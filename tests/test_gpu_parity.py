@@ -173,3 +173,42 @@ def test_error_mapping_on_device(ops):
         ops.matmul248(torch.zeros(1, 64).half().cuda(), *cuda(qw, s, qz, g), 4, 15)
     with pytest.raises(ValueError, match='cuda'):
         ops.matmul248(torch.zeros(1, 128).half(), qw, s, qz, g, 4, 15)
+
+
+# ----------------------------------------------------------------------------- batched (prefill) path: tcgen05 GEMM
+@pytest.mark.parametrize('M,K,N,gs', [(16, 512, 256, 128), (100, 1024, 384, 64), (128, 256, 128, 128), (300, 2048, 512, 128), (129, 128, 128, 64)])
+def test_prefill_gemm_vs_oracle(ops, M, K, N, gs):
+    """M > 8, int4, no act-order: tcgen05 GEMM (qgemm_tcgen05.cu) against the CPU oracle."""
+    qw, s, qz, g, b = O.random_packed(K, N, 4, gs, seed=M + K, bias=(M % 2 == 0))
+    x = torch.randn(M, K, generator=torch.Generator().manual_seed(M)).half()
+    ref = O.qlinear_fwd(x, qw, s, qz, g, 4, b)
+    out = ops.matmul248(x.cuda(), *cuda(qw, s, qz, g), 4, 15, bias=b.cuda() if b is not None else None, groupsize=gs)
+    # tensor-core fp32 accumulation is not IEEE round-to-nearest per add (the reference's tl.dot has the same property): allow 2 fp16 ulps
+    assert_rel_close(out, ref, rel=2e-3, what=f'prefill M={M} K={K} N={N} gs={gs}')
+
+
+def test_prefill_gemm_full_size_matches_dequant_matmul(ops):
+    """LLaMA-7B layer size, M = 512: tcgen05 GEMM == fp32 matmul over the device-dequantised weight; exact homogeneity."""
+    K, N, M = 4096, 4096, 512
+    qw, s, qz, g, _ = cuda(*O.random_packed(K, N, 4, 128, seed=3))
+    x = torch.randn(M, K, generator=torch.Generator().manual_seed(0)).half().cuda()
+    W = ops.dequant(qw, s, qz, g, 4, 128)
+    ref = (x.float() @ W.float()).half()
+    out = ops.matmul248(x, qw, s, qz, g, 4, 15, groupsize=128)
+    assert_rel_close(out, ref, rel=2e-3, what='prefill full size')
+    out2 = ops.matmul248(x * 2, qw, s, qz, g, 4, 15, groupsize=128)
+    normal = out.abs() > 1e-3  # fp16 subnormal results do not scale exactly
+    assert torch.equal(out2[normal], (out * 2)[normal])
+    assert torch.equal(ops.matmul248(x, qw, s, qz, g, 4, 15, groupsize=128), out)  # deterministic
+
+
+@pytest.mark.parametrize('M', [24, 200])
+def test_prefill_fused_mlp_vs_oracle(ops, M):
+    """Fused SwiGLU MLP at M > 8: dual-accumulator tcgen05 GEMM, silu*mul on the fp32 accumulators in the epilogue."""
+    K, N, gs = 512, 384, 128
+    gate = O.random_packed(K, N, 4, gs, seed=1)[:4]
+    up = O.random_packed(K, N, 4, gs, seed=2)[:4]
+    x = (torch.randn(M, K, generator=torch.Generator().manual_seed(3)) * 2).half()
+    ref = O.fused_mlp_fwd(x, gate, up, 4)
+    out = ops.fused_mlp(x.cuda(), cuda(*gate), cuda(*up), 4, gs)
+    assert_rel_close(out, ref, rel=3e-3, what=f'prefill fused mlp M={M}')
