@@ -1,0 +1,87 @@
+"""CPU, world_size 2, gloo: the host logic of tensor-parallel QuantLinear (sharding + collectives).  The local matvec
+is replaced by the oracle here (there is no GPU); the GPU version of this test is tests/test_gpu_tp.py."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import gptq_oracle as O
+
+
+def test_partitions():
+    from gptq_b200 import tp
+    assert tp.column_partition(4096, 8) == [512 * i for i in range(9)]
+    b = tp.column_partition(22016, 8)  # 65B gate/up: 2752 columns per rank
+    assert b[-1] == 22016 and all((b[i + 1] - b[i]) % 32 == 0 for i in range(8)) and max(b[i + 1] - b[i] for i in range(8)) == 2752
+    r = tp.row_partition(22016, 128, 8)  # 65B down_proj: 172 groups -> 21 or 22 groups per rank
+    sizes = [r[i + 1] - r[i] for i in range(8)]
+    assert r[0] == 0 and r[-1] == 22016 and set(sizes) == {21 * 128, 22 * 128}
+    with pytest.raises(ValueError):
+        tp.row_partition(100, 128, 2)
+    bytes_per_rank = tp.per_rank_bytes(22016, 8192, 4, 128, 8, 'row')
+    assert abs(sum(bytes_per_rank) - (22016 * 8192 // 2 + 172 * 8192 * 2 + 172 * 8192 // 2)) < 1e-6
+
+
+def test_shards_reassemble():
+    from gptq_b200 import tp
+    K, N, bits, gs = 512, 256, 4, 128
+    qw, s, qz, g, b = O.random_packed(K, N, bits, gs, seed=1, bias=True)
+    x = torch.randn(3, K, generator=torch.Generator().manual_seed(0)).half()
+    full = O.qlinear_fwd(x, qw, s, qz, g, bits)
+    cols = [O.qlinear_fwd(x, *tp.shard_columns(qw, s, qz, g, bits, r, 4)[:4], bits) for r in range(4)]
+    assert torch.equal(torch.cat(cols, dim=1), full)  # column shards are exact
+    acc = torch.zeros(3, N)
+    for r in range(4):
+        sqw, ss, sqz, sg, (k0, k1) = tp.shard_rows(qw, s, qz, g, bits, gs, r, 4)
+        W = O.dequant(sqw, ss, sqz, sg, bits)
+        assert torch.equal(W, O.dequant(qw, s, qz, g, bits)[k0:k1])  # a row shard dequantises to the same weights
+        acc += x[:, k0:k1].float() @ W.float()
+    assert torch.allclose(acc.half().float(), full.float(), rtol=1e-3, atol=1e-3)
+    with pytest.raises(ValueError):
+        tp.shard_rows(qw, s, qz, O.make_g_idx(K, gs, True, torch.Generator().manual_seed(0)), bits, gs, 0, 2)
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        import quant
+        from gptq_b200 import tp
+        K, N, bits, gs = 512, 256, 4, 128
+        qw, s, qz, g, b = O.random_packed(K, N, bits, gs, seed=1, bias=True)
+        full = quant.QuantLinear(bits, gs, K, N, True)
+        full.qweight, full.scales, full.qzeros, full.g_idx, full.bias = qw, s, qz, g, b
+        x = torch.randn(3, K, generator=torch.Generator().manual_seed(0)).half()
+        ref = O.qlinear_fwd(x, qw, s, qz, g, bits, b)
+
+        def cpu_forward(layer):  # test-only stand-in for the CUDA kernel
+            return lambda inp: O.qlinear_fwd(inp, layer.qweight, layer.scales, layer.qzeros, layer.g_idx, layer.bits, layer.bias)
+
+        col = tp.TPQuantLinear(full, 'column', gather_output=True)
+        col.local.forward = cpu_forward(col.local)
+        out_c = col(x)
+        row = tp.TPQuantLinear(full, 'row')
+        row.local.forward = cpu_forward(row.local)
+        out_r = row(x)
+        ok = torch.equal(out_c, ref) and torch.allclose(out_r.float(), ref.float(), rtol=2e-3, atol=2e-3)
+        ok = ok and col.local.outfeatures == N // world and row.local.infeatures == K // world
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp_quantlinear_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(2))
+    assert res == {0: True, 1: True}
