@@ -40,7 +40,8 @@ constexpr int kRowPitch = 1024 + 32;   // smem pitch of a 1 KB weight row: +32 B
 constexpr int kTile = 4 * kRowPitch;   // one ring stage: 4 packed rows x 256 columns of one matrix (4 KB of weights)
 constexpr int kStages = 15;            // 15 x 4224 B = 63,360 B of weights in flight per CTA
 constexpr int kHD = 128;
-constexpr int kAttnChunk = 128;  // keys per attention work item
+constexpr int kAttnChunk = 256;  // keys per attention work item (two passes of 128 with an online-softmax merge)
+constexpr int kAttnPass = 128;
 constexpr int kRec = kHD + 4;     // floats per split-KV partial record: m, l, 2 pad, o[128] (keeps o 16-byte aligned)
 constexpr int kMaxLayers = 80;
 
@@ -504,60 +505,72 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
         }
         cta_sync();
         const int grp = tid >> 3, j = tid & 7;  // 32 groups of 8 lanes; lane j owns dims [16j, 16j+16)
-        constexpr int ITER = kAttnChunk / 32;
-        // all K and V rows of this lane are requested up front (clamped indices): two DRAM round trips per item, not one per key
-        uint4 kreg[ITER][2], vreg[ITER][2];
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int tk = min(c0 + grp + it * 32, c1 - 1);
-            const uint4* kp = reinterpret_cast<const uint4*>(kc + (size_t)tk * kHD + 16 * j);
-            kreg[it][0] = kp[0];
-            kreg[it][1] = kp[1];
-        }
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int tk = min(c0 + grp + it * 32, c1 - 1);
-            const uint4* vp = reinterpret_cast<const uint4*>(vc + (size_t)tk * kHD + 16 * j);
-            vreg[it][0] = vp[0];
-            vreg[it][1] = vp[1];
-        }
+        constexpr int ITER = kAttnPass / 32;
         float qr[16];
 #pragma unroll
         for (int d = 0; d < 16; ++d) qr[d] = q_s[16 * j + d];
-        float sc[ITER];
-        float mloc = -INFINITY;
-#pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int tk = c0 + grp + it * 32;
-            const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w, kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float2 f = __half22float2(u32_as_h2(w[e]));
-                s = fmaf(qr[2 * e], f.x, s);
-                s = fmaf(qr[2 * e + 1], f.y, s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            s = (tk < c1) ? s * p.scale : -INFINITY;
-            sc[it] = s;
-            mloc = fmaxf(mloc, s);
-        }
-        float lloc = 0.f, o[16];
+        // running online-softmax state of this lane group over the item's passes
+        float mloc = -INFINITY, lloc = 0.f, o[16];
 #pragma unroll
         for (int d = 0; d < 16; ++d) o[d] = 0.f;
+#pragma unroll 1
+        for (int p0 = c0; p0 < c1; p0 += kAttnPass) {
+            // all K and V rows of this lane for the pass are requested up front (clamped indices): two DRAM round trips per pass
+            uint4 kreg[ITER][2], vreg[ITER][2];
 #pragma unroll
-        for (int it = 0; it < ITER; ++it) {
-            const int tk = c0 + grp + it * 32;
-            const float pw = (tk < c1) ? expf(sc[it] - mloc) : 0.f;
-            lloc += pw;
-            const uint32_t w[8] = {vreg[it][0].x, vreg[it][0].y, vreg[it][0].z, vreg[it][0].w, vreg[it][1].x, vreg[it][1].y, vreg[it][1].z, vreg[it][1].w};
+            for (int it = 0; it < ITER; ++it) {
+                const int tk = min(p0 + grp + it * 32, c1 - 1);
+                const uint4* kp = reinterpret_cast<const uint4*>(kc + (size_t)tk * kHD + 16 * j);
+                kreg[it][0] = kp[0];
+                kreg[it][1] = kp[1];
+            }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float2 f = __half22float2(u32_as_h2(w[e]));
-                o[2 * e] = fmaf(pw, f.x, o[2 * e]);
-                o[2 * e + 1] = fmaf(pw, f.y, o[2 * e + 1]);
+            for (int it = 0; it < ITER; ++it) {
+                const int tk = min(p0 + grp + it * 32, c1 - 1);
+                const uint4* vp = reinterpret_cast<const uint4*>(vc + (size_t)tk * kHD + 16 * j);
+                vreg[it][0] = vp[0];
+                vreg[it][1] = vp[1];
+            }
+            float sc[ITER];
+            float mpass = -INFINITY;
+#pragma unroll
+            for (int it = 0; it < ITER; ++it) {
+                const int tk = p0 + grp + it * 32;
+                const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w, kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
+                float s = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float2 f = __half22float2(u32_as_h2(w[e]));
+                    s = fmaf(qr[2 * e], f.x, s);
+                    s = fmaf(qr[2 * e + 1], f.y, s);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                s = (tk < c1) ? s * p.scale : -INFINITY;
+                sc[it] = s;
+                mpass = fmaxf(mpass, s);
+            }
+            const float mnew = fmaxf(mloc, mpass);
+            if (mnew != -INFINITY) {
+                const float alpha = (mloc == -INFINITY) ? 0.f : expf(mloc - mnew);
+                lloc *= alpha;
+#pragma unroll
+                for (int d = 0; d < 16; ++d) o[d] *= alpha;
+#pragma unroll
+                for (int it = 0; it < ITER; ++it) {
+                    const int tk = p0 + grp + it * 32;
+                    const float pw = (tk < c1) ? expf(sc[it] - mnew) : 0.f;
+                    lloc += pw;
+                    const uint32_t w[8] = {vreg[it][0].x, vreg[it][0].y, vreg[it][0].z, vreg[it][0].w, vreg[it][1].x, vreg[it][1].y, vreg[it][1].z, vreg[it][1].w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        const float2 f = __half22float2(u32_as_h2(w[e]));
+                        o[2 * e] = fmaf(pw, f.x, o[2 * e]);
+                        o[2 * e + 1] = fmaf(pw, f.y, o[2 * e + 1]);
+                    }
+                }
+                mloc = mnew;
             }
         }
         if (j == 0) {
