@@ -14,6 +14,9 @@
 //   epilogue         : tcgen05.ld 32x32b -> fp16 (+ bias) -> global
 //
 // Numerics: fp16 operands identical to the reference's (exact dequant), fp32 accumulation in TMEM, one fp16 rounding.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "int4_core.cuh"
 #include "kernels.h"
@@ -24,9 +27,11 @@ namespace {
 using namespace int4;
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStagesG = 3;
+constexpr int kStagesG = 4;   // shared-memory ring depth
+constexpr int kAhead = 2;     // operands are requested kAhead K-steps before they are consumed (hides ~1.5 us of L2/DRAM latency)
 constexpr int kTileBytes = BM * BK * 2;  // 16 KB (A and B tiles have the same size)
-constexpr int kGemmThreads = 256;
+constexpr int kGemmThreads = 256;              // producer threads: A staging + B dequantisation, later the epilogue
+constexpr int kGemmBlock = kGemmThreads + 64;  // + one warp issuing the tcgen05.mma stream + one warp issuing the TMA loads of A
 
 // instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = F16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t kIdesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -76,19 +81,22 @@ struct GemmParams {
 };
 
 // DUAL: out = silu(x.Wg) * (x.Wu) with both fp32 accumulators in TMEM (fusedmatmul_248_kernel, quant/fused_mlp.py:84-168)
-template <bool DUAL>
-__global__ void __launch_bounds__(kGemmThreads, 1) qgemm_tcgen05_kernel(const GemmParams p) {
+// MT: M tiles of 128 rows per CTA (1 or 2).  With MT = 2 every dequantised B tile feeds two MMAs (256 rows), which halves the
+// CUDA-core dequant work per tensor-core flop -- the limiter of the MT = 1 configuration.
+template <bool DUAL, int MT>
+__global__ void __launch_bounds__(kGemmBlock, 1) qgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const GemmParams p) {
     constexpr int NW = DUAL ? 2 : 1;
-    constexpr uint32_t kTmemCols = 128 * NW;
+    constexpr uint32_t kTmemCols = 128 * NW * MT;  // accumulator (weight w, M tile mt) lives at column 128 * (w * MT + mt)
+    constexpr int kATile = MT * kTileBytes;
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ __align__(8) unsigned long long bars[kStagesG + 1];
+    __shared__ __align__(8) unsigned long long bars[2 * kStagesG + 1];  // empty[S] (MMA -> producers), acc_done, full[S] (producers -> MMA)
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * (BM * MT), n0 = blockIdx.x * BN;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024 B alignment
     uint8_t* sptr = smem_raw + (sbase - smem_u32(smem_raw));
-    const uint32_t a_s = sbase, b_s = sbase + kStagesG * kTileBytes;  // B tiles: [stage][weight]
-    uint8_t* b_ptr = sptr + kStagesG * kTileBytes;
+    const uint32_t a_s = sbase, b_s = sbase + kStagesG * kATile;  // A tiles: [stage][MT x 128 rows]; B tiles: [stage][weight]
+    uint8_t* b_ptr = sptr + kStagesG * kATile;
     const uint32_t bar0 = smem_u32(&bars[0]);
 
     if (warp == 0) {
@@ -97,6 +105,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) qgemm_tcgen05_kernel(const Ge
     }
     if (tid == 0) {
         for (int i = 0; i <= kStagesG; ++i) mbar_init(bar0 + i * 8, 1);
+        for (int i = 0; i < kStagesG; ++i) mbar_init(bar0 + (kStagesG + 1 + i) * 8, kGemmThreads + 1);  // 256 B-producers + the TMA thread's expect_tx
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -104,41 +114,84 @@ __global__ void __launch_bounds__(kGemmThreads, 1) qgemm_tcgen05_kernel(const Ge
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
+    const uint32_t full0 = bar0 + (kStagesG + 1) * 8;
+    const int nkb = p.K / BK;
+    if (warp == kGemmThreads / 32) {
+        // ===== MMA issuer: one elected lane streams tcgen05.mma; tcgen05.commit releases each stage and finally the accumulator =====
+        if (lane == 0) {
+#pragma unroll 1
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % kStagesG;
+                mbar_wait(full0 + s * 8, (it / kStagesG) & 1u);  // all 256 producers have filled this stage
+                tc_fence_after();
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const uint64_t bd = smem_desc(b_s + (s * NW + w) * kTileBytes);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint64_t ad = smem_desc(a_s + s * kATile + mt * kTileBytes);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 inside the swizzle atom
+                            tc_mma(tmem + 128 * (w * MT + mt), ad + 2 * k, bd + 2 * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar0 + s * 8);
+                if (it + 1 == nkb) tc_commit(bar0 + kStagesG * 8);  // accumulator complete
+            }
+        }
+        tc_fence_before();
+        __syncthreads();  // matches the producers' barrier before the TMEM dealloc
+        return;
+    }
+
+    if (warp == kGemmThreads / 32 + 1) {
+        // ===== TMA producer for A: box 64 (k) x 128 (rows), SWIZZLE_128B = exactly the canonical K-major layout; rows beyond M are zero-filled =====
+        if (lane == 0) {
+#pragma unroll 1
+            for (int it = 0; it < nkb; ++it) {
+                const int s = it % kStagesG;
+                if (it >= kStagesG) mbar_wait(bar0 + s * 8, ((it / kStagesG) - 1) & 1u);  // MMAs that read this stage are done
+                mbar_expect_tx(full0 + s * 8, MT * kTileBytes);
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                                     a_s + s * kATile + mt * kTileBytes),
+                                 "l"(&tmA), "r"(it * BK), "r"(m0 + 128 * mt), "r"(full0 + s * 8)
+                                 : "memory");
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
+
     // ---- per-thread roles ---------------------------------------------------------------------------------------
     // A: 1024 chunks of 16 B per stage, 4 per thread: chunk id = tid + 256 i -> row id >> 3, k-chunk id & 7
     // B: column n = tid & 127, k-chunks c = (tid >> 7) + 2 i
     const int bn = tid & 127, bc0 = tid >> 7;
     const int col = n0 + bn;
     const int zshift = (col & 7) * 4;
-    const int nkb = p.K / BK;
 
-    auto load_a = [&](int it, int s) {
-        const int k0 = it * BK;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int id = tid + kGemmThreads * i;
-            const int r = id >> 3, c = id & 7;
-            const __half* src = p.x + (size_t)min(m0 + r, p.M - 1) * p.ldx + k0 + c * 8;
-            cp_async16(a_s + s * kTileBytes + r * 128 + ((c ^ (r & 7)) << 4), src);
-        }
-        cp_async_commit();
-    };
-    uint32_t bq[NW][4];
-    auto load_b = [&](int it) {
+    uint32_t bq[kAhead + 1][NW][4];  // packed words of K steps it .. it + kAhead (a register ring, rotated every step)
+    auto load_b = [&](int it, uint32_t (&dst)[NW][4]) {
         const int kr0 = it * (BK / 8);
 #pragma unroll
         for (int w = 0; w < NW; ++w)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) bq[w][i] = __ldg(p.qw[w] + col + (size_t)(kr0 + bc0 + 2 * i) * p.N);
+            for (int i = 0; i < 4; ++i) dst[w][i] = __ldg(p.qw[w] + col + (size_t)(kr0 + bc0 + 2 * i) * p.N);
     };
 
     int cur_grp = -1;
     __half2 za[NW], zb[NW], sc2[NW];
-    load_a(0, 0);
-    load_b(0);
+#pragma unroll
+    for (int d = 0; d < kAhead; ++d) {
+        if (d < nkb) load_b(d, bq[d]);
+    }
 #pragma unroll 1
     for (int it = 0; it < nkb; ++it) {
         const int s = it % kStagesG;
+        // ---- first: request the packed words of step it + kAhead (A arrives by TMA from the producer warp) -------
+        if (it + kAhead < nkb) load_b(it + kAhead, bq[kAhead]);
         if (it >= kStagesG) mbar_wait(bar0 + s * 8, ((it / kStagesG) - 1) & 1u);  // the MMAs that read this stage have completed
         // ---- dequantise this step's packed words into the B tile --------------------------------------------------
         const int grp = (it * BK) / p.groupsize;
@@ -159,7 +212,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) qgemm_tcgen05_kernel(const Ge
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 uint32_t v[4];  // (k0,k4) (k1,k5) (k2,k6) (k3,k7)
-                dequant8<0>(bq[w][i], za[w], zb[w], sc2[w], v);
+                dequant8<0>(bq[0][w][i], za[w], zb[w], sc2[w], v);
                 uint4 o;
                 o.x = __byte_perm(v[0], v[1], 0x5410);  // (k0,k1)
                 o.y = __byte_perm(v[2], v[3], 0x5410);  // (k2,k3)
@@ -169,31 +222,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) qgemm_tcgen05_kernel(const Ge
                 *reinterpret_cast<uint4*>(b_ptr + (s * NW + w) * kTileBytes + bn * 128 + ((c ^ (bn & 7)) << 4)) = o;
             }
         }
-        // ---- prefetch the next step (its stage was released by MMAs two steps back) -------------------------------
-        if (it + 1 < nkb) {
-            const int s1 = (it + 1) % kStagesG;
-            if (it + 1 >= kStagesG) mbar_wait(bar0 + s1 * 8, (((it + 1) / kStagesG) - 1) & 1u);
-            load_a(it + 1, s1);
-            load_b(it + 1);
-            cp_async_wait<1>();  // A(it) has landed; A(it+1) may still be in flight
-        } else {
-            cp_async_wait<0>();
-        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint64_t ad = smem_desc(a_s + s * kTileBytes);
+        mbar_arrive(full0 + s * 8);  // no block-wide barrier in the loop: the MMA warp waits for 256 arrivals
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                const uint64_t bd = smem_desc(b_s + (s * NW + w) * kTileBytes);
+        for (int d = 0; d < kAhead; ++d)
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 inside the swizzle atom
-                    tc_mma(tmem + 128 * w, ad + 2 * k, bd + 2 * k, kIdesc, (it > 0 || k > 0) ? 1u : 0u);
-            }
-            tc_commit(bar0 + s * 8);
-            if (it + 1 == nkb) tc_commit(bar0 + kStagesG * 8);  // accumulator complete
-        }
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bq[d][w][i] = bq[d + 1][w][i];
     }
 
     // ---- epilogue: TMEM -> registers -> fp16 (+bias) -> global -------------------------------------------------------
@@ -201,15 +237,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) qgemm_tcgen05_kernel(const Ge
     tc_fence_after();
     {
         const int q = warp & 3, half = warp >> 2;  // a warp may only touch TMEM lanes [32 (warp % 4), +32)
-        const int row = m0 + 32 * q + lane;
 #pragma unroll 1
-        for (int j = 0; j < 2; ++j) {
+        for (int jj = 0; jj < 2 * MT; ++jj) {
+            const int mt = jj >> 1, j = jj & 1;
+            const int row = m0 + 128 * mt + 32 * q + lane;
             const int c0 = 64 * half + 32 * j;
             uint32_t r[32];
-            tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
+            tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * mt + c0), r);
             if constexpr (DUAL) {  // silu(gate) * up on the fp32 accumulators, one rounding (quant/fused_mlp.py:163-165)
                 uint32_t r2[32];
-                tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 + c0), r2);
+                tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)(128 * (MT + mt) + c0), r2);
 #pragma unroll
                 for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(swiglu(__uint_as_float(r[e]), __uint_as_float(r2[e])));
             }
@@ -252,7 +289,26 @@ bool gemm_tc_supported(const QLinearArgs& a) {
     return true;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked: the library must load without a driver)
+static bool make_x_tensor_map(CUtensorMap* tm, const void* x, int M, int K, int64_t ldx) {
+    static PFN_cuTensorMapEncodeTiled encode = []() -> PFN_cuTensorMapEncodeTiled {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    }();
+    if (encode == nullptr) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};   // innermost first
+    const cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};         // bytes between rows
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};  // 64 halves (128 B) x 128 rows
+    const cuuint32_t estr[2] = {1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_qlinear_gemm_tc(const QLinearArgs& a) {
+    CUtensorMap tmA;
+    if (!make_x_tensor_map(&tmA, a.x, a.M, a.w.K, a.ldx)) return cudaErrorNotSupported;
     GemmParams p{};
     p.x = reinterpret_cast<const __half*>(a.x);
     p.ldx = a.ldx;
@@ -268,19 +324,17 @@ cudaError_t launch_qlinear_gemm_tc(const QLinearArgs& a) {
     p.out = reinterpret_cast<__half*>(a.out);
     p.ldo = a.ldo;
     p.M = a.M; p.K = a.w.K; p.N = a.w.N; p.groupsize = a.w.groupsize;
-    const size_t smem = 1024 + (size_t)(a.dual ? 3 : 2) * kStagesG * kTileBytes;
-    const dim3 grid(a.w.N / BN, ceil_div(a.M, BM));
-    cudaError_t e;
-    if (a.dual) {
-        e = cudaFuncSetAttribute(qgemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int mt = (a.M > BM && !a.dual) ? 2 : 1;  // the dual kernel keeps two B tiles per stage: 128-row tiles leave room for 4 stages
+    const size_t smem = 1024 + (size_t)(mt + (a.dual ? 2 : 1)) * kStagesG * kTileBytes;
+    const dim3 grid(a.w.N / BN, ceil_div(a.M, BM * mt));
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        qgemm_tcgen05_kernel<true><<<grid, kGemmThreads, smem, a.stream>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(qgemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        qgemm_tcgen05_kernel<false><<<grid, kGemmThreads, smem, a.stream>>>(p);
-    }
-    return cudaGetLastError();
+        kernel<<<grid, kGemmBlock, smem, a.stream>>>(tmA, p);
+        return cudaGetLastError();
+    };
+    if (a.dual) return mt == 2 ? go(qgemm_tcgen05_kernel<true, 2>) : go(qgemm_tcgen05_kernel<true, 1>);
+    return mt == 2 ? go(qgemm_tcgen05_kernel<false, 2>) : go(qgemm_tcgen05_kernel<false, 1>);
 }
 
 }  // namespace gptq
