@@ -154,3 +154,22 @@ def test_column_slices_are_independent():
     for n0, n1 in ((0, 128), (128, 512), (256, 288)):
         part = ops.matmul248(x, qw[:, n0:n1].contiguous(), s[:, n0:n1].contiguous(), qz[:, n0 // 8:n1 // 8].contiguous(), g, 4, 15)
         assert_rel_close(part, full[:, n0:n1], what=f'cols {n0}:{n1}')
+
+
+def test_act_order_plan_uses_tuned_kernels_and_matches_gather_path():
+    """Act-order int4: the load-time row regrouping (derived buffer + x gather) gives the same result as the g_idx-gather kernel."""
+    import quant
+    from gptq_b200 import ops
+    ql = quant.QuantLinear(4, 128, 1024, 512, False)
+    _fill(ql, 4, seed=11, act=True)
+    x = torch.randn(3, 1024, generator=torch.Generator().manual_seed(2)).half()
+    ref = O.qlinear_fwd(x, ql.qweight, ql.scales, ql.qzeros, ql.g_idx, 4)
+    ql = ql.cuda()
+    assert quant.autotune_warmup_linear(ql) == 1 and ql.act_order_plan() is not None
+    perm, qw_sorted, g_triv = ql.act_order_plan()
+    W_gather = ops.dequant(ql.qweight, ql.scales, ql.qzeros, ql.g_idx, 4, 0)
+    W_sorted = ops.dequant(qw_sorted, ql.scales, ql.qzeros, g_triv, 4, 128)
+    assert torch.equal(W_sorted, W_gather.index_select(0, perm))  # the same fp16 weights, rows regrouped
+    assert_rel_close(ql(x.cuda()), ref, what='act-order fast path M=3')
+    xb = torch.randn(40, 1024, generator=torch.Generator().manual_seed(3)).half()
+    assert_rel_close(ql(xb.cuda()), O.qlinear_fwd(xb, *(t.cpu() for t in (ql.qweight, ql.scales, ql.qzeros, ql.g_idx)), 4), rel=2e-3, what='act-order fast path M=40')
