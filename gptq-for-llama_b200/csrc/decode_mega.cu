@@ -44,6 +44,10 @@ constexpr int kAttnChunk = 256;  // keys per attention work item (two passes of 
 constexpr int kAttnPass = 128;
 constexpr int kRec = kHD + 4;     // floats per split-KV partial record: m, l, 2 pad, o[128] (keeps o 16-byte aligned)
 constexpr int kMaxLayers = 80;
+#ifndef GPTQ_STEP_UNROLL
+#define GPTQ_STEP_UNROLL 2
+#endif
+constexpr int kStepUnroll = GPTQ_STEP_UNROLL;  // unroll factor of the per-tile loop (development knob)
 
 #ifdef GPTQ_TRACE
 }  // namespace
@@ -404,7 +408,7 @@ __device__ void run_matvec(const MegaParams& p, Pipe& pipe, const MatDesc& w0, c
         uint4 q_cur;
         uint32_t bar_cur;
         fetch(q_cur, bar_cur);
-#pragma unroll 1
+#pragma unroll kStepUnroll
         for (int step = 0; step < nsteps; ++step) {
             if (steps_left_in_grp == 0) {
 #pragma unroll
