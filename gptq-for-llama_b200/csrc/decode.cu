@@ -436,7 +436,12 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
 
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     uint8_t* sc = reinterpret_cast<uint8_t*>(st->scratch);
-    if (mega_supported(m, *st)) return launch_decode_mega(m, *st, sc + L.mega, stream) == cudaSuccess ? GPTQ_OK : GPTQ_ERR_CUDA;
+    if (mega_supported(m, *st)) {
+        const cudaError_t e = launch_decode_mega(m, *st, sc + L.mega, stream);
+        if (e == cudaSuccess) return GPTQ_OK;
+        if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
+        // the device cannot co-schedule the persistent grid (or the shape does not fit its staging buffers): per-op kernel chain below
+    }
     __half* x = reinterpret_cast<__half*>(sc + L.x);
     __half* qkv = reinterpret_cast<__half*>(sc + L.qkv);
     __half* attn = reinterpret_cast<__half*>(sc + L.attn);

@@ -852,12 +852,17 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     const size_t xs_halves = (size_t)m.hidden;  // segments of the down projection are far shorter than H (checked below)
     const size_t tmp_bytes = max((size_t)m.hidden * 2, (size_t)(192 + 32 * 132) * 4);
     const size_t smem = (size_t)(((kStages * kTile + 127) / 128) * 128) + xs_halves * 2 + tmp_bytes;
-    const int grid = 2 * kNumSMs;
+    // cooperative launch: every CTA must be co-resident (2 per SM on B200); if the device cannot host them, the caller
+    // falls back to the kernel-chain engine instead of risking a barrier deadlock
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaErrorInvalidDevice;
+    cudaError_t e = cudaFuncSetAttribute(llama_decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llama_decode_mega_kernel, kBlock, smem) != cudaSuccess || occ < 1) return cudaErrorCooperativeLaunchTooLarge;
+    const int grid = (occ >= 2 ? 2 : 1) * sms;
     // the per-CTA k-segment of the down projection must fit in xs
     const long long seg_steps = ((long long)(m.hidden / kSlabCols) * (m.intermediate / 32) + grid - 1) / grid;
     if (seg_steps * 32 > (long long)xs_halves || smem > 110 * 1024) return cudaErrorInvalidConfiguration;
-    cudaError_t e = cudaFuncSetAttribute(llama_decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kBlock);
