@@ -27,7 +27,6 @@ namespace {
 using namespace int4;
 
 constexpr int BM = 128, BN = 128, BK = 64;
-constexpr int kStagesG = 4;   // shared-memory ring depth
 constexpr int kAhead = 2;     // operands are requested kAhead K-steps before they are consumed (hides ~1.5 us of L2/DRAM latency)
 constexpr int kTileBytes = BM * BK * 2;  // 16 KB (A and B tiles have the same size)
 constexpr int kGemmThreads = 256;              // producer threads: A staging + B dequantisation, later the epilogue
@@ -83,7 +82,7 @@ struct GemmParams {
 // DUAL: out = silu(x.Wg) * (x.Wu) with both fp32 accumulators in TMEM (fusedmatmul_248_kernel, quant/fused_mlp.py:84-168)
 // MT: M tiles of 128 rows per CTA (1 or 2).  With MT = 2 every dequantised B tile feeds two MMAs (256 rows), which halves the
 // CUDA-core dequant work per tensor-core flop -- the limiter of the MT = 1 configuration.
-template <bool DUAL, int MT>
+template <bool DUAL, int MT, int kStagesG>
 __global__ void __launch_bounds__(kGemmBlock, 1) qgemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const GemmParams p) {
     constexpr int NW = DUAL ? 2 : 1;
     constexpr uint32_t kTmemCols = 128 * NW * MT;  // accumulator (weight w, M tile mt) lives at column 128 * (w * MT + mt)
@@ -324,8 +323,9 @@ cudaError_t launch_qlinear_gemm_tc(const QLinearArgs& a) {
     p.out = reinterpret_cast<__half*>(a.out);
     p.ldo = a.ldo;
     p.M = a.M; p.K = a.w.K; p.N = a.w.N; p.groupsize = a.w.groupsize;
-    const int mt = (a.M > BM && !a.dual) ? 2 : 1;  // the dual kernel keeps two B tiles per stage: 128-row tiles leave room for 4 stages
-    const size_t smem = 1024 + (size_t)(mt + (a.dual ? 2 : 1)) * kStagesG * kTileBytes;
+    const int mt = a.M > BM ? 2 : 1;
+    const int stages = (a.dual && mt == 2) ? 3 : 4;  // 256-row dual tiles: 64 KB per stage -> 3 stages; everything else 4
+    const size_t smem = 1024 + (size_t)(mt + (a.dual ? 2 : 1)) * stages * kTileBytes;
     const dim3 grid(a.w.N / BN, ceil_div(a.M, BM * mt));
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -333,8 +333,8 @@ cudaError_t launch_qlinear_gemm_tc(const QLinearArgs& a) {
         kernel<<<grid, kGemmBlock, smem, a.stream>>>(tmA, p);
         return cudaGetLastError();
     };
-    if (a.dual) return mt == 2 ? go(qgemm_tcgen05_kernel<true, 2>) : go(qgemm_tcgen05_kernel<true, 1>);
-    return mt == 2 ? go(qgemm_tcgen05_kernel<false, 2>) : go(qgemm_tcgen05_kernel<false, 1>);
+    if (a.dual) return mt == 2 ? go(qgemm_tcgen05_kernel<true, 2, 3>) : go(qgemm_tcgen05_kernel<true, 1, 4>);
+    return mt == 2 ? go(qgemm_tcgen05_kernel<false, 2, 4>) : go(qgemm_tcgen05_kernel<false, 1, 4>);
 }
 
 }  // namespace gptq
