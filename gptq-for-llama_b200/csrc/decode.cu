@@ -396,9 +396,16 @@ extern "C" size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int ba
     return scratch_layout(*model, batch, max_seq).total;
 }
 
+static bool has_input_perm(const gptq_llama_model& m) {
+    for (int l = 0; l < m.n_layers; ++l)
+        if (m.layers[l].qkv_perm != nullptr || m.layers[l].o_perm != nullptr || m.layers[l].mlp_perm != nullptr) return true;
+    return false;
+}
+
 extern "C" int gptq_llama_decode_launches(const gptq_llama_model* model, const gptq_llama_state* st) {
     if (model == nullptr || st == nullptr || model->layers == nullptr) return GPTQ_ERR_NULL;
     if (mega_supported(*model, *st)) return 1;
+    if (has_input_perm(*model)) return GPTQ_ERR_UNSUPPORTED;  // regrouped act-order layers need the persistent kernel's gathers
     int n = 1 + 2 + (st->next_tokens != nullptr ? 1 : 0) - 1;  // embed + lm_head (+ argmax)
     n = 1 + 1 + (st->next_tokens != nullptr ? 1 : 0);
     for (int l = 0; l < model->n_layers; ++l) {
@@ -442,6 +449,7 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
         if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
         // the device cannot co-schedule the persistent grid (or the shape does not fit its staging buffers): per-op kernel chain below
     }
+    if (has_input_perm(m)) return GPTQ_ERR_UNSUPPORTED;
     __half* x = reinterpret_cast<__half*>(sc + L.x);
     __half* qkv = reinterpret_cast<__half*>(sc + L.qkv);
     __half* attn = reinterpret_cast<__half*>(sc + L.attn);

@@ -77,6 +77,9 @@ struct LayerDesc {
     MatDesc qkv, o, gate, up, down;
     const __half* input_norm;
     const __half* post_norm;
+    const int32_t* qkv_perm;  // act-order input gathers (gptq_llama_layer), nullptr = identity
+    const int32_t* o_perm;
+    const int32_t* mlp_perm;
 };
 struct MegaParams {
     int n_layers, H, I, V, n_heads, groupsize, max_seq, nsplit;
@@ -237,8 +240,10 @@ __device__ __forceinline__ void store_perm8(__half* dst, uint32_t w0, uint32_t w
 
 // x = rmsnorm(src [+ fp16(acc)]) for the whole row (K = H), staged k-permuted in xs; the updated residual stream
 // (src + fp16(acc)) is written to resid_out by slices.  src/acc/resid_out are global.
+// ACT: the matvec's packed rows were regrouped by the host (act-order): position k' of xs holds feature perm[k'].
+template <bool ACT>
 __device__ void stage_norm(const MegaParams& p, const __half* src, const float* acc, const __half* norm_w, __half* resid_out, __half* xs, __half* tmp,
-                           float* red_s) {
+                           float* red_s, const int32_t* perm) {
     const int H = p.H, tid = threadIdx.x;
     float ss = 0.f;
     for (int c = tid; c < H / 8; c += kThreads) {
@@ -263,6 +268,22 @@ __device__ void stage_norm(const MegaParams& p, const __half* src, const float* 
     const float rstd = 1.0f / sqrtf(tot / (float)H + p.eps);
     const int per = (H / 8 + gridDim.x - 1) / gridDim.x;
     const int wlo = blockIdx.x * per, whi = min(H / 8, wlo + per);
+    if constexpr (ACT) {
+        if (perm != nullptr) {
+            for (int c = tid; c < H / 8; c += kThreads) {
+                if (resid_out != nullptr && c >= wlo && c < whi) *reinterpret_cast<uint4*>(resid_out + c * 8) = *reinterpret_cast<const uint4*>(tmp + c * 8);
+                __half o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = perm[c * 8 + j];
+                    o[j] = __float2half_rn(__fmul_rn(__fmul_rn(__half2float(tmp[k]), rstd), __half2float(norm_w[k])));
+                }
+                const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
+                store_perm8(xs + c * 8, ow[0], ow[1], ow[2], ow[3]);
+            }
+            return;
+        }
+    }
     for (int c = tid; c < H / 8; c += kThreads) {
         const uint4 v = *reinterpret_cast<const uint4*>(tmp + c * 8);
         if (resid_out != nullptr && c >= wlo && c < whi) *reinterpret_cast<uint4*>(resid_out + c * 8) = v;
@@ -282,9 +303,9 @@ enum XMode { X_FULL = 0, X_ATTN = 1, X_SWIGLU = 2 };
 
 // One matvec op for this CTA: consume the tiles of its unit range from the ring, RED the results.
 // xs holds either the full K row (X_FULL, staged by stage_norm before the call) or is (re)staged per segment here.
-template <bool DUAL, int XMODE>
+template <bool DUAL, int XMODE, bool ACT = false>
 __device__ void run_matvec(const MegaParams& p, Pipe& pipe, const MatDesc& w0, const MatDesc& w1, int K, int N,
-                           float* out0, float* out1, __half* xs) {
+                           float* out0, float* out1, __half* xs, const int32_t* perm = nullptr) {
     constexpr int NW = DUAL ? 2 : 1;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const unsigned nk = K / 32, U = (unsigned)(N / kSlabCols) * nk, nb = gridDim.x;
@@ -343,7 +364,10 @@ __device__ void run_matvec(const MegaParams& p, Pipe& pipe, const MatDesc& w0, c
             } else {  // attention output: one thread per feature combines the split-KV partials of its head (coalesced over d)
                 const int nvalid = min(p.nsplit, p.positions[0] / kAttnChunk + 1);
                 for (int e = tid; e < nsteps * 32; e += kThreads) {
-                    const int k = kbeg + e;
+                    int k = kbeg + e;
+                    if constexpr (ACT) {
+                        if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
+                    }
                     const int head = k / kHD, d = k - head * kHD;
                     const float* src = p.part + (size_t)head * p.nsplit * kRec;
                     float M = -INFINITY;
@@ -605,6 +629,7 @@ __device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
     }
 }
 
+template <bool ACT>
 __global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __grid_constant__ MegaParams p) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ float red_s[kWarps];
@@ -658,7 +683,7 @@ __global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __gr
         const LayerDesc& L = p.layers[l];
         // ---- Q ----
         MTRACE(l * 12 + 0);
-        stage_norm(p, resid_src, resid_acc, L.input_norm, p.resid[cur ^ 1], xs, tmp, red_s);
+        stage_norm<ACT>(p, resid_src, resid_acc, L.input_norm, p.resid[cur ^ 1], xs, tmp, red_s, L.qkv_perm);
         MTRACE(l * 12 + 1);
         cur ^= 1;
         zero_slice(p.acc_g, p.I);  // last read by the previous layer's D
@@ -676,12 +701,12 @@ __global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __gr
         MTRACE(l * 12 + 5);
         // ---- O ----
         zero_slice(p.acc_qkv, 3 * p.H);
-        run_matvec<false, X_ATTN>(p, pipe, L.o, L.o, p.H, p.H, p.acc_o, nullptr, xs);
+        run_matvec<false, X_ATTN, ACT>(p, pipe, L.o, L.o, p.H, p.H, p.acc_o, nullptr, xs, L.o_perm);
         MTRACE(l * 12 + 6);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 7);
         // ---- G ----
-        stage_norm(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, tmp, red_s);
+        stage_norm<ACT>(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, tmp, red_s, L.mlp_perm);
         cur ^= 1;
         cta_sync();
         MTRACE(l * 12 + 8);
@@ -698,7 +723,7 @@ __global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __gr
         resid_acc = p.acc_d;
     }
     // ---- L: final norm + lm_head (fp16 [V, H] rows, one warp per row) ----
-    stage_norm(p, resid_src, resid_acc, p.final_norm, nullptr, xs, tmp, red_s);
+    stage_norm<false>(p, resid_src, resid_acc, p.final_norm, nullptr, xs, tmp, red_s, nullptr);
     zero_slice(p.acc_g, p.I);
     zero_slice(p.acc_u, p.I);
     cta_sync();
@@ -781,6 +806,7 @@ bool mega_supported(const gptq_llama_model& m, const gptq_llama_state& st) {
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         const gptq_qweight* ws[5] = {&ly.qkv, &ly.o, &ly.gate, &ly.up, &ly.down};
+        if ((ly.qkv_perm != nullptr || ly.o_perm != nullptr || ly.mlp_perm != nullptr) && (m.hidden % 8 != 0)) return false;
         for (const gptq_qweight* w : ws) {
             if (w->bits != 4 || w->groupsize != gs) return false;
             if ((reinterpret_cast<uintptr_t>(w->qweight) & 15) || (reinterpret_cast<uintptr_t>(w->scales) & 7)) return false;
@@ -831,6 +857,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     p.part = reinterpret_cast<float*>(take((size_t)m.n_heads * p.nsplit * kRec * 4));
     p.rope_cs = reinterpret_cast<float*>(take(128 * 4));
     p.bar = reinterpret_cast<unsigned long long*>(take(256));
+    bool act = false;  // any act-order gather: the ACT instantiation (the plain one carries no trace of the feature)
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         auto md = [](const gptq_qweight& w) {
@@ -847,6 +874,10 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
         p.layers[l].down = md(ly.down);
         p.layers[l].input_norm = reinterpret_cast<const __half*>(ly.input_norm);
         p.layers[l].post_norm = reinterpret_cast<const __half*>(ly.post_norm);
+        p.layers[l].qkv_perm = ly.qkv_perm;
+        p.layers[l].o_perm = ly.o_perm;
+        p.layers[l].mlp_perm = ly.mlp_perm;
+        act = act || ly.qkv_perm != nullptr || ly.o_perm != nullptr || ly.mlp_perm != nullptr;
     }
     // smem: rings + xs (max(H, widest staged segment)) + tmp (H halves or the attention scratch)
     const size_t xs_halves = (size_t)m.hidden;  // segments of the down projection are far shorter than H (checked below)
@@ -856,9 +887,10 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     // falls back to the kernel-chain engine instead of risking a barrier deadlock
     int dev = 0, sms = 0, occ = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaErrorInvalidDevice;
-    cudaError_t e = cudaFuncSetAttribute(llama_decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kernel = act ? llama_decode_mega_kernel<true> : llama_decode_mega_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, llama_decode_mega_kernel, kBlock, smem) != cudaSuccess || occ < 1) return cudaErrorCooperativeLaunchTooLarge;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) return cudaErrorCooperativeLaunchTooLarge;
     const int grid = (occ >= 2 ? 2 : 1) * sms;
     // the per-CTA k-segment of the down projection must fit in xs
     const long long seg_steps = ((long long)(m.hidden / kSlabCols) * (m.intermediate / 32) + grid - 1) / grid;
@@ -873,7 +905,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, llama_decode_mega_kernel, p);
+    return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
 }  // namespace gptq

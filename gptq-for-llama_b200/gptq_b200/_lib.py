@@ -35,7 +35,8 @@ _QW = ctypes.POINTER(QWeight)
 
 class LlamaLayer(ctypes.Structure):
     """struct gptq_llama_layer."""
-    _fields_ = [('qkv', QWeight), ('o', QWeight), ('gate', QWeight), ('up', QWeight), ('down', QWeight), ('input_norm', c_void_p), ('post_norm', c_void_p)]
+    _fields_ = [('qkv', QWeight), ('o', QWeight), ('gate', QWeight), ('up', QWeight), ('down', QWeight), ('input_norm', c_void_p), ('post_norm', c_void_p),
+                ('qkv_perm', c_void_p), ('o_perm', c_void_p), ('mlp_perm', c_void_p)]
 
 
 class LlamaModel(ctypes.Structure):

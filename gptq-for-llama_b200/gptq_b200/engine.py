@@ -34,7 +34,21 @@ class QLayerWeights:
         self.qweight, self.scales, self.qzeros, self.g_idx, self.bits = qweight.contiguous(), scales.contiguous(), qzeros.contiguous(), g_idx.contiguous(), bits
         K = qweight.shape[0] * 32 // bits
         self.g_idx = self.g_idx[:K].contiguous()
+        self.groupsize = groupsize
         self.hint = groupsize if ops.is_trivial_g_idx(self.g_idx, groupsize) else 0
+
+    def kernel_form(self, allow_perm=True):
+        """(layer in the layout the tuned int4 kernels take, input gather or None); see ops.kernel_form."""
+        plan = ops.kernel_form(self.qweight, self.scales, self.qzeros, self.g_idx, self.bits, self.groupsize, allow_perm=allow_perm)
+        if plan is None:
+            return self, None
+        return QLayerWeights(plan['qweight'], self.scales, plan['qzeros'], plan['g_idx'], plan['bits'], self.groupsize), plan['perm']
+
+    def permute_columns(self, perm):
+        """The same layer with output columns reordered: out'[:, j] = out[:, perm[j]] (used to fold the NEXT layer's input gather)."""
+        zeros = ops.unpack_qzeros(self.qzeros, self.bits).index_select(1, perm)
+        return QLayerWeights(self.qweight.index_select(1, perm), self.scales.index_select(1, perm), ops.pack_qzeros(zeros, self.bits), self.g_idx, self.bits,
+                             self.groupsize)
 
     @classmethod
     def from_module(cls, m):
@@ -62,6 +76,27 @@ def random_qlayer(K, N, bits, groupsize, device, gen, act_order=False):
     return QLayerWeights(qw, s, qz, g, bits, groupsize)
 
 
+def kernel_layers(layers, allow_perm=True):
+    """Load-time preparation of a layer stack for the decode kernels (the stored tensors stay as they are):
+    2/3-bit fields widened to nibbles and act-order rows regrouped (ops.kernel_form).  The input gathers this needs are
+    returned per layer for the kernel (qkv, o, gate|up); down_proj's gather costs nothing at run time: it is folded into
+    the column order of gate|up, whose SwiGLU output then comes out in down_proj's regrouped order.
+    Returns (prepared layers, perms) or None when gate and up do not share their act-order map."""
+    out, perms = [], []
+    for ly in layers:
+        k, pm = {}, {}
+        for name in ('qkv', 'o', 'gate', 'up', 'down'):
+            k[name], pm[name] = ly[name].kernel_form(allow_perm)
+        if (pm['gate'] is None) != (pm['up'] is None) or (pm['gate'] is not None and not torch.equal(pm['gate'], pm['up'])):
+            return None
+        if pm['down'] is not None:
+            k['gate'], k['up'] = k['gate'].permute_columns(pm['down']), k['up'].permute_columns(pm['down'])
+        k['input_norm'], k['post_norm'] = ly['input_norm'], ly['post_norm']
+        out.append(k)
+        perms.append({n: (pm[n].to(torch.int32).contiguous() if pm[n] is not None else None) for n in ('qkv', 'o', 'gate')})
+    return out, perms
+
+
 class LlamaDecoder:
     """Owns the weights, the KV cache and the captured graph; `step()` decodes one token per sequence."""
 
@@ -75,12 +110,13 @@ class LlamaDecoder:
         self.intermediate = layers[0]['gate'].qweight.shape[1]
         self.batch, self.max_seq = batch, max_seq
         with torch.cuda.device(self.dev):
+            # kernel-side view of the weights: nibble-widened 2/3-bit fields, regrouped act-order rows (+ input gathers)
+            prepared = kernel_layers(layers, allow_perm=(batch == 1))
+            if prepared is None:
+                prepared = kernel_layers(layers, allow_perm=False)
+            self.klayers, self.perms = prepared
             self._layer_arr = (LlamaLayer * len(layers))()
-            for i, ly in enumerate(layers):
-                for name in ('qkv', 'o', 'gate', 'up', 'down'):
-                    setattr(self._layer_arr[i], name, ly[name].struct())
-                self._layer_arr[i].input_norm = ly['input_norm'].data_ptr()
-                self._layer_arr[i].post_norm = ly['post_norm'].data_ptr()
+            self._fill_layer_structs()
             m = LlamaModel()
             m.n_layers, m.hidden, m.n_heads, m.head_dim = len(layers), self.hidden, n_heads, self.hidden // n_heads
             m.intermediate, m.vocab, m.rms_eps, m.rope_base = self.intermediate, self.vocab, rms_eps, rope_base
@@ -105,11 +141,26 @@ class LlamaDecoder:
             st.logits, st.next_tokens = self.logits.data_ptr(), self.next_tokens.data_ptr()
             st.scratch, st.scratch_bytes = self.scratch.data_ptr(), nbytes
             self.state = st
+            if any(p is not None for pm in self.perms for p in pm.values()) and self.launches_per_step() != 1:
+                # the input gathers exist only in the persistent kernel: act-order layers go back to their stored form
+                self.klayers, self.perms = kernel_layers(layers, allow_perm=False)
+                self._fill_layer_structs()
         self.n_launches = None
         self.graph = None
         self._stream = torch.cuda.Stream(self.dev)
         if use_graph:
             self._capture()
+
+    def _fill_layer_structs(self):
+        for i, ly in enumerate(self.klayers):
+            for name in ('qkv', 'o', 'gate', 'up', 'down'):
+                setattr(self._layer_arr[i], name, ly[name].struct())
+            self._layer_arr[i].input_norm = ly['input_norm'].data_ptr()
+            self._layer_arr[i].post_norm = ly['post_norm'].data_ptr()
+            pm = self.perms[i]
+            self._layer_arr[i].qkv_perm = pm['qkv'].data_ptr() if pm['qkv'] is not None else None
+            self._layer_arr[i].o_perm = pm['o'].data_ptr() if pm['o'] is not None else None
+            self._layer_arr[i].mlp_perm = pm['gate'].data_ptr() if pm['gate'] is not None else None
 
     # ------------------------------------------------------------------------------------------
     def _enqueue(self, stream):
@@ -170,10 +221,13 @@ def synthetic_llama(size='7b', bits=4, groupsize=128, act_order=False, vocab=320
     gen = torch.Generator(device=dev).manual_seed(seed)
     L = []
     for _ in range(layers):
+        gate = random_qlayer(hidden, inter, bits, groupsize, dev, gen, act_order)
+        up = random_qlayer(hidden, inter, bits, groupsize, dev, gen, act_order)
+        if act_order:  # gate and up see the same input, hence the same Hessian diagonal and the same act-order map (gptq.py:210-216)
+            up = QLayerWeights(up.qweight, up.scales, up.qzeros, gate.g_idx.clone(), bits, groupsize)
         L.append(
             dict(qkv=random_qlayer(hidden, 3 * hidden, bits, groupsize, dev, gen, act_order), o=random_qlayer(hidden, hidden, bits, groupsize, dev, gen, act_order),
-                 gate=random_qlayer(hidden, inter, bits, groupsize, dev, gen, act_order), up=random_qlayer(hidden, inter, bits, groupsize, dev, gen, act_order),
-                 down=random_qlayer(inter, hidden, bits, groupsize, dev, gen, act_order),
+                 gate=gate, up=up, down=random_qlayer(inter, hidden, bits, groupsize, dev, gen, act_order),
                  input_norm=(torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half(),
                  post_norm=(torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half()))
     # q/k/v share their input, hence their act-order map (quant/fused_attn.py:180): nothing to do, qkv is one layer here

@@ -221,3 +221,39 @@ def unpack_qzeros(qzeros, bits):
         out = torch.empty((G, N), device=qzeros.device, dtype=torch.int32)
         check(lib.gptq_unpack_qzeros(qzeros.contiguous().data_ptr(), out.data_ptr(), G, N, bits, _stream(qzeros)))
     return out
+
+
+def kernel_form(qweight, scales, qzeros, g_idx, bits, groupsize, allow_perm=True):
+    """Load-time derived buffers that let the tuned int4 kernels (matvec, tcgen05 GEMM, persistent decode kernel)
+    serve a layer they would otherwise leave to the generic kernel.  The stored tensors are not touched.
+
+    * act-order (arbitrary g_idx, gptq.py:210-216) with equal-sized groups: the packed rows are regrouped so that every
+      group is contiguous (k' = rank of k in a stable sort by group); the caller feeds x'[k'] = x[perm[k']].  Every
+      weight keeps its own scale/zero, so the products are the same numbers; only the fp32 summation order changes.
+    * bits 2 or 3: every field is widened to a nibble (same integers, same stored-minus-one zeros), i.e. the layer is
+      re-expressed in the int4 layout.  This trades 33 % (int3) / 100 % (int2) more weight bytes for the tuned kernels;
+      a native 3-bit streaming kernel is the follow-up.
+
+    Returns None when nothing applies, else a dict(qweight, qzeros, g_idx, bits, perm) -- perm is an int64 tensor or None.
+    """
+    _require_cuda(qweight)
+    K, N = qweight.shape[0] * 32 // bits, qweight.shape[1]
+    trivial = is_trivial_g_idx(g_idx, groupsize)
+    perm, rows = None, None
+    if not trivial:
+        g = g_idx[:K].long()
+        G = scales.shape[0]
+        if not allow_perm or K % groupsize or G * groupsize != K or not bool((torch.bincount(g, minlength=G) == groupsize).all()):
+            return None
+        perm = torch.argsort(g, stable=True)
+        rows = unpack_qweight(qweight, bits).index_select(0, perm)
+    widen = bits in (2, 3)
+    if perm is None and not widen:
+        return None
+    new_bits = 4 if widen else bits
+    if rows is None:
+        rows = unpack_qweight(qweight, bits)
+    new_qweight = pack_qweight(rows, new_bits)
+    new_qzeros = pack_qzeros(unpack_qzeros(qzeros, bits), 4) if widen else qzeros
+    g_triv = (torch.arange(K, device=qweight.device) // groupsize).to(torch.int32)
+    return dict(qweight=new_qweight, qzeros=new_qzeros, g_idx=g_triv, bits=new_bits, perm=perm)

@@ -72,7 +72,7 @@ class QuantLinear(nn.Module):
             self.bias = None
         self._g_key = None  # cache key of the act-order probe
         self._g_trivial = False
-        self._sorted = None  # act-order fast path: (perm, qweight with rows regrouped, trivial g_idx), derived lazily
+        self._sorted = None  # (cache key, ops.kernel_form result), derived lazily
 
     # ------------------------------------------------------------------ packing (offline)
     def pack(self, linear, scales, zeros, g_idx=None):
@@ -115,37 +115,27 @@ class QuantLinear(nn.Module):
             self._g_key = key
         return self.groupsize if self._g_trivial else 0
 
-    def act_order_plan(self):
-        """Derived buffers that turn an act-order layer (arbitrary g_idx, gptq.py:210-216) into a trivial-g_idx one without
-        touching the stored tensors: rows of the weight are regrouped so that every group is contiguous (k' = rank of k in a
-        stable sort by group) and x is gathered with the same permutation.  Each weight keeps its own scale/zero, so the
-        products are the same numbers; only the fp32 summation order changes.  Returns None when not applicable
-        (groups of unequal size): the gather kernel is used then."""
-        if self._sorted is not None and self._sorted[0] == (self.g_idx.data_ptr(), self.qweight.data_ptr()):
-            return self._sorted[1]
-        K, gs = self.infeatures, self.groupsize
-        g = self.g_idx[:K].long()
-        counts = torch.bincount(g, minlength=math.ceil(K / gs))
-        plan = None
-        if K % gs == 0 and bool((counts == gs).all()):
-            perm = torch.argsort(g, stable=True)
-            rows = ops.unpack_qweight(self.qweight, self.bits)  # [K, N] int32 on the device
-            plan = (perm, ops.pack_qweight(rows.index_select(0, perm), self.bits), (torch.arange(K, device=g.device) // gs).to(torch.int32))
-        self._sorted = ((self.g_idx.data_ptr(), self.qweight.data_ptr()), plan)
-        return plan
+    def kernel_plan(self):
+        """Derived buffers (gptq_b200.ops.kernel_form) that route an act-order and/or 2/3-bit layer to the tuned int4
+        kernels without touching the stored tensors; None when the layer needs none or does not qualify."""
+        key = (self.g_idx.data_ptr(), self.g_idx._version, self.qweight.data_ptr(), self.qweight._version, self.qzeros.data_ptr())
+        if self._sorted is None or self._sorted[0] != key:
+            self._sorted = (key, ops.kernel_form(self.qweight, self.scales, self.qzeros, self.g_idx, self.bits, self.groupsize))
+        return self._sorted[1]
+
+    act_order_plan = kernel_plan  # earlier name
 
     def forward(self, x):
         out_shape = x.shape[:-1] + (self.outfeatures, )
         x2 = x.reshape(-1, x.shape[-1])
-        hint = self.groupsize_hint()
-        if hint == 0 and self.qweight.is_cuda:
-            plan = self.act_order_plan()
-            if plan is not None:  # act-order: regrouped rows + gathered x -> the tuned trivial-g_idx kernels
-                perm, qweight_sorted, g_trivial = plan
-                out = QuantLinearFunction.apply(x2.index_select(1, perm), qweight_sorted, self.scales, self.qzeros, g_trivial, self.bits, self.maxq, self.bias,
-                                                self.groupsize)
-                return out.reshape(out_shape)
-        out = QuantLinearFunction.apply(x2, self.qweight, self.scales, self.qzeros, self.g_idx, self.bits, self.maxq, self.bias, hint)
+        plan = self.kernel_plan() if self.qweight.is_cuda else None
+        if plan is not None:  # regrouped rows (+ gathered x) and/or nibble-widened fields -> the tuned trivial-g_idx int4 kernels
+            if plan['perm'] is not None:
+                x2 = x2.index_select(1, plan['perm'])
+            out = QuantLinearFunction.apply(x2, plan['qweight'], self.scales, plan['qzeros'], plan['g_idx'], plan['bits'], 2**plan['bits'] - 1, self.bias,
+                                            self.groupsize)
+            return out.reshape(out_shape)
+        out = QuantLinearFunction.apply(x2, self.qweight, self.scales, self.qzeros, self.g_idx, self.bits, self.maxq, self.bias, self.groupsize_hint())
         return out.reshape(out_shape)
 
 
@@ -171,7 +161,7 @@ def autotune_warmup_linear(model, transpose=False):
     n = 0
     for _, m in model.named_modules():
         if isinstance(m, QuantLinear) and m.qweight.is_cuda:
-            if m.groupsize_hint() == 0:
-                m.act_order_plan()  # regroup act-order rows once, at load time
+            m.groupsize_hint()
+            m.kernel_plan()  # regroup act-order rows / widen 2- and 3-bit fields once, at load time
             n += 1
     return n

@@ -127,6 +127,14 @@ typedef struct gptq_llama_layer {
     gptq_qweight o, gate, up, down;
     const void* input_norm;  /* fp16 [hidden] */
     const void* post_norm;   /* fp16 [hidden] */
+    /* Optional input gathers (device int32, NULL = identity) for act-order layers whose packed rows the host has
+     * regrouped at load time so that every quantisation group is contiguous (g_idx then is the trivial k / groupsize
+     * map): the matvec reads x'[k'] = x[perm[k']].  q|k|v share one map, gate|up share one map (same input, hence same
+     * act-order, quant/fused_attn.py:180); down_proj's map is folded into the column order of gate|up by the host.
+     * Only the persistent single-kernel path implements the gathers; otherwise GPTQ_ERR_UNSUPPORTED is returned. */
+    const int32_t* qkv_perm; /* [hidden] */
+    const int32_t* o_perm;   /* [hidden] */
+    const int32_t* mlp_perm; /* [hidden] */
 } gptq_llama_layer;
 
 typedef struct gptq_llama_model {

@@ -48,13 +48,18 @@ def _oracle_decode(dec, token_ids):
 
 
 @pytest.mark.parametrize('size,bits,act,use_graph', [('tiny', 4, False, True), ('tiny', 4, False, False), ('tiny', 4, True, True), ('tiny', 8, False, True),
-                                                     ('tiny', 3, True, True), ('tiny256', 4, False, True), ('tiny256', 4, False, False)])
+                                                     ('tiny', 3, True, True), ('tiny256', 4, False, True), ('tiny256', 4, False, False),
+                                                     ('tiny256', 4, True, True), ('tiny256', 3, True, True), ('tiny256', 3, False, True), ('tiny256', 2, True, False)])
 def test_decode_steps_match_oracle(size, bits, act, use_graph):
     from gptq_b200 import engine
     dec = engine.synthetic_llama(size, bits=bits, groupsize=64, act_order=act, vocab=512, seed=bits, max_seq=600, use_graph=use_graph)
-    assert dec.launches_per_step() == (1 if (size == 'tiny256' and bits == 4 and not act) else dec.launches_per_step())
     if size == 'tiny256':
-        assert dec.launches_per_step() == 1  # persistent single-kernel path
+        # persistent single-kernel path, also for act-order (regrouped rows + input gathers) and 2/3-bit (nibble-widened) layers
+        assert dec.launches_per_step() == 1
+        assert all(k['qkv'].bits == 4 and k['qkv'].hint == 64 for k in dec.klayers)
+        assert (dec.perms[0]['qkv'] is not None) == act
+    else:
+        assert dec.launches_per_step() > 1 and all(pm['qkv'] is None for pm in dec.perms)
     gen = torch.Generator().manual_seed(0)
     toks = torch.randint(0, 512, (6, ), generator=gen).tolist()
     ref = _oracle_decode(dec, toks)

@@ -165,11 +165,33 @@ def test_act_order_plan_uses_tuned_kernels_and_matches_gather_path():
     x = torch.randn(3, 1024, generator=torch.Generator().manual_seed(2)).half()
     ref = O.qlinear_fwd(x, ql.qweight, ql.scales, ql.qzeros, ql.g_idx, 4)
     ql = ql.cuda()
-    assert quant.autotune_warmup_linear(ql) == 1 and ql.act_order_plan() is not None
-    perm, qw_sorted, g_triv = ql.act_order_plan()
+    assert quant.autotune_warmup_linear(ql) == 1 and ql.kernel_plan() is not None
+    plan = ql.kernel_plan()
+    perm, qw_sorted, g_triv = plan['perm'], plan['qweight'], plan['g_idx']
+    assert plan['bits'] == 4 and plan['qzeros'] is ql.qzeros
     W_gather = ops.dequant(ql.qweight, ql.scales, ql.qzeros, ql.g_idx, 4, 0)
     W_sorted = ops.dequant(qw_sorted, ql.scales, ql.qzeros, g_triv, 4, 128)
     assert torch.equal(W_sorted, W_gather.index_select(0, perm))  # the same fp16 weights, rows regrouped
     assert_rel_close(ql(x.cuda()), ref, what='act-order fast path M=3')
     xb = torch.randn(40, 1024, generator=torch.Generator().manual_seed(3)).half()
     assert_rel_close(ql(xb.cuda()), O.qlinear_fwd(xb, *(t.cpu() for t in (ql.qweight, ql.scales, ql.qzeros, ql.g_idx)), 4), rel=2e-3, what='act-order fast path M=40')
+
+
+@pytest.mark.parametrize('bits,act', [(3, False), (3, True), (2, True)])
+def test_narrow_bits_are_served_by_the_int4_kernels_through_the_widened_plan(bits, act):
+    """2/3-bit layers (config 4: int3 act-order): fields widened to nibbles at load time -> identical dequantised weights,
+    outputs within tolerance of the oracle on the ORIGINAL packed tensors, for the matvec (M=1) and the GEMM (M=40)."""
+    import quant
+    from gptq_b200 import ops
+    ql = quant.QuantLinear(bits, 128, 1024, 512, False)
+    _fill(ql, bits, seed=20 + bits, act=act)
+    cpu = [t.clone() for t in (ql.qweight, ql.scales, ql.qzeros, ql.g_idx)]
+    ql = ql.cuda()
+    plan = ql.kernel_plan()
+    assert plan is not None and plan['bits'] == 4 and (plan['perm'] is not None) == act
+    W_orig = ops.dequant(ql.qweight, ql.scales, ql.qzeros, ql.g_idx, bits, 0)
+    W_plan = ops.dequant(plan['qweight'], ql.scales, plan['qzeros'], plan['g_idx'], 4, 128)
+    assert torch.equal(W_plan, W_orig if plan['perm'] is None else W_orig.index_select(0, plan['perm']))
+    for M, rel in ((1, 1e-3), (40, 2e-3)):
+        x = torch.randn(M, 1024, generator=torch.Generator().manual_seed(M)).half()
+        assert_rel_close(ql(x.cuda()), O.qlinear_fwd(x, *cpu, bits), rel=rel, what=f'bits={bits} act={act} M={M}')
