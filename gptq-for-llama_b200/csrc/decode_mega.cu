@@ -270,16 +270,22 @@ __device__ void stage_norm(const MegaParams& p, const __half* src, const float* 
     const int wlo = blockIdx.x * per, whi = min(H / 8, wlo + per);
     if constexpr (ACT) {
         if (perm != nullptr) {
+            // norm_w is given in regrouped order (gptq_b200.h): the index vector and the weights travel together, the gather
+            // itself reads shared memory
             for (int c = tid; c < H / 8; c += kThreads) {
                 if (resid_out != nullptr && c >= wlo && c < whi) *reinterpret_cast<uint4*>(resid_out + c * 8) = *reinterpret_cast<const uint4*>(tmp + c * 8);
-                __half o[8];
+                const ::int4 p0 = *reinterpret_cast<const ::int4*>(perm + c * 8), p1 = *reinterpret_cast<const ::int4*>(perm + c * 8 + 4);
+                const uint4 nw = *reinterpret_cast<const uint4*>(norm_w + c * 8);
+                const int k[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                const uint32_t wv[4] = {nw.x, nw.y, nw.z, nw.w};
+                uint32_t o[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = perm[c * 8 + j];
-                    o[j] = __float2half_rn(__fmul_rn(__fmul_rn(__half2float(tmp[k]), rstd), __half2float(norm_w[k])));
+                for (int j = 0; j < 4; ++j) {
+                    const float2 wf = __half22float2(u32_as_h2(wv[j]));
+                    const float x0 = __half2float(tmp[k[2 * j]]), x1 = __half2float(tmp[k[2 * j + 1]]);
+                    o[j] = h2_as_u32(__floats2half2_rn(__fmul_rn(__fmul_rn(x0, rstd), wf.x), __fmul_rn(__fmul_rn(x1, rstd), wf.y)));
                 }
-                const uint32_t* ow = reinterpret_cast<const uint32_t*>(o);
-                store_perm8(xs + c * 8, ow[0], ow[1], ow[2], ow[3]);
+                store_perm8(xs + c * 8, o[0], o[1], o[2], o[3]);
             }
             return;
         }

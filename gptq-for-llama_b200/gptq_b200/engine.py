@@ -91,7 +91,9 @@ def kernel_layers(layers, allow_perm=True):
             return None
         if pm['down'] is not None:
             k['gate'], k['up'] = k['gate'].permute_columns(pm['down']), k['up'].permute_columns(pm['down'])
-        k['input_norm'], k['post_norm'] = ly['input_norm'], ly['post_norm']
+        # per-input-feature vectors of a regrouped matvec are handed over in regrouped order
+        k['input_norm'] = ly['input_norm'] if pm['qkv'] is None else ly['input_norm'].index_select(0, pm['qkv']).contiguous()
+        k['post_norm'] = ly['post_norm'] if pm['gate'] is None else ly['post_norm'].index_select(0, pm['gate']).contiguous()
         out.append(k)
         perms.append({n: (pm[n].to(torch.int32).contiguous() if pm[n] is not None else None) for n in ('qkv', 'o', 'gate')})
     return out, perms

@@ -131,6 +131,8 @@ typedef struct gptq_llama_layer {
      * regrouped at load time so that every quantisation group is contiguous (g_idx then is the trivial k / groupsize
      * map): the matvec reads x'[k'] = x[perm[k']].  q|k|v share one map, gate|up share one map (same input, hence same
      * act-order, quant/fused_attn.py:180); down_proj's map is folded into the column order of gate|up by the host.
+     * With qkv_perm set, input_norm is given in the same regrouped order (input_norm'[k'] = input_norm[perm[k']]);
+     * likewise post_norm with mlp_perm.
      * Only the persistent single-kernel path implements the gathers; otherwise GPTQ_ERR_UNSUPPORTED is returned. */
     const int32_t* qkv_perm; /* [hidden] */
     const int32_t* o_perm;   /* [hidden] */
