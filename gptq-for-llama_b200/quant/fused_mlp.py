@@ -37,6 +37,19 @@ class QuantLlamaMLP(nn.Module):
         self.down_proj = down_proj
         self._g_key = None
         self._g_trivial = False
+        self._plan = None  # (cache key, derived gate/up buffers for the tuned kernels or None)
+
+    def kernel_plan(self):
+        """gate/up in the layout of the tuned int4 kernels (ops.kernel_form: act-order rows regrouped, 2/3-bit fields widened) when
+        both qualify and share their input gather (same input, hence the same act-order map); None otherwise."""
+        key = tuple((t.data_ptr(), t._version) for t in (self.gate_proj_qweight, self.up_proj_qweight, self.gate_proj_g_idx, self.up_proj_g_idx))
+        if self._plan is None or self._plan[0] != key:
+            pg = ops.kernel_form(self.gate_proj_qweight, self.gate_proj_scales, self.gate_proj_qzeros, self.gate_proj_g_idx, self.bits, self.groupsize)
+            pu = ops.kernel_form(self.up_proj_qweight, self.up_proj_scales, self.up_proj_qzeros, self.up_proj_g_idx, self.bits, self.groupsize)
+            ok = pg is not None and pu is not None and ((pg['perm'] is None and pu['perm'] is None) or
+                                                        (pg['perm'] is not None and pu['perm'] is not None and torch.equal(pg['perm'], pu['perm'])))
+            self._plan = (key, (pg, pu) if ok else None)
+        return self._plan[1]
 
     def forward(self, x):
         return self.down_proj(self.triton_llama_mlp(x))
@@ -52,6 +65,15 @@ class QuantLlamaMLP(nn.Module):
     def triton_llama_mlp(self, x):
         """fp16 [..., intermediate] = silu(x.Wgate) * (x.Wup).  The name is the reference's (:206); no Triton is involved."""
         out_shape = x.shape[:-1] + (self.intermediate_size, )
+        plan = self.kernel_plan() if self.gate_proj_qweight.is_cuda else None
+        if plan is not None:
+            pg, pu = plan
+            x2 = x.reshape(-1, x.shape[-1])
+            if pg['perm'] is not None:
+                x2 = x2.index_select(1, pg['perm'])
+            c = ops.fused_mlp(x2, (pg['qweight'], self.gate_proj_scales, pg['qzeros'], pg['g_idx']), (pu['qweight'], self.up_proj_scales, pu['qzeros'], pu['g_idx']),
+                              pg['bits'], self.groupsize)
+            return c.reshape(out_shape)
         c = ops.fused_mlp(x.reshape(-1, x.shape[-1]), tuple(getattr(self, f'gate_proj_{p}') for p in _PARTS),
                           tuple(getattr(self, f'up_proj_{p}') for p in _PARTS), self.bits, self.groupsize_hint())
         return c.reshape(out_shape)
@@ -90,5 +112,6 @@ def autotune_warmup_fused(model):
     for _, m in model.named_modules():
         if isinstance(m, QuantLlamaMLP) and m.gate_proj_qweight.is_cuda:
             m.groupsize_hint()
+            m.kernel_plan()
             n += 1
     return n

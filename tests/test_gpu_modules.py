@@ -88,12 +88,12 @@ def _ref_forward(model, ids):
     return (h.float() @ model.lm_head.weight.data.float().t())
 
 
-@pytest.mark.parametrize('act', [False, True])
-def test_load_quant_pipeline_on_tiny_llama(act):
+@pytest.mark.parametrize('bits,act', [(4, False), (4, True), (3, True)])
+def test_load_quant_pipeline_on_tiny_llama(bits, act):
     """make_quant_linear -> (load) -> make_quant_attn / make_quant_norm / make_fused_mlp -> .to(DEV) -> forward,
     prefill then one cached decode step, against the oracle-composed reference."""
     import quant
-    model = _tiny_quant_llama(act=act)
+    model = _tiny_quant_llama(bits=bits, act=act)
     ids = torch.randint(0, 256, (1, 9), generator=torch.Generator().manual_seed(0))
     ref_logits = _ref_forward(model, ids)
     quant.make_quant_attn(model)
@@ -101,6 +101,8 @@ def test_load_quant_pipeline_on_tiny_llama(act):
     quant.make_fused_mlp(model)
     model = model.cuda()
     assert quant.autotune_warmup_linear(model) > 0 and quant.autotune_warmup_fused(model) == 2
+    if act or bits != 4:  # derived buffers route act-order / 3-bit layers to the tuned kernels
+        assert model.model.layers[0].mlp.kernel_plan() is not None and model.model.layers[0].self_attn.qkv_proj.kernel_plan() is not None
     with torch.no_grad():
         out = model(ids[:, :8].cuda(), use_cache=True)
         assert_rel_close(out.logits[0], ref_logits[0, :8], rel=2e-2, what='prefill logits')
