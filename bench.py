@@ -28,7 +28,7 @@ import torch  # noqa: E402
 
 METRIC = 'tokens/sec LLaMA-7B int4 g128 batch=1; matvec HBM GB/s vs 8 TB/s roofline'
 SEQ = 2048
-NCU_TRAFFIC_BYTES = 4447960888  # per launch of llama_decode_mega_kernel: 4.4524 GB read + 13.0 MB written (profiles/r1_mega_final_summary.txt)
+NCU_TRAFFIC_BYTES = 4447960888  # per launch of llama_decode_mega_kernel: 4.4350 GB read + 12.9 MB written (profiles/r1_mega_final_summary.txt)
 BITS, GROUP = 4, 128
 
 
