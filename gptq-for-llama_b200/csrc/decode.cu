@@ -406,8 +406,7 @@ extern "C" int gptq_llama_decode_launches(const gptq_llama_model* model, const g
     if (model == nullptr || st == nullptr || model->layers == nullptr) return GPTQ_ERR_NULL;
     if (mega_supported(*model, *st)) return 1;
     if (has_input_perm(*model)) return GPTQ_ERR_UNSUPPORTED;  // regrouped act-order layers need the persistent kernel's gathers
-    int n = 1 + 2 + (st->next_tokens != nullptr ? 1 : 0) - 1;  // embed + lm_head (+ argmax)
-    n = 1 + 1 + (st->next_tokens != nullptr ? 1 : 0);
+    int n = 1 + 1 + (st->next_tokens != nullptr ? 1 : 0);  // embed + lm_head (+ argmax)
     for (int l = 0; l < model->n_layers; ++l) {
         const gptq_llama_layer& ly = model->layers[l];
         const gptq_qweight* ws[4] = {&ly.qkv, &ly.o, &ly.gate, &ly.down};

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GPTQ_B200_ABI_VERSION 1
+#define GPTQ_B200_ABI_VERSION 2 /* 2: gptq_llama_layer gained the act-order input gathers */
 
 typedef void* gptq_stream_t; /* cudaStream_t */
 
