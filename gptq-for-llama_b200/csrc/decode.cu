@@ -443,7 +443,15 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     uint8_t* sc = reinterpret_cast<uint8_t*>(st->scratch);
     if (mega_supported(m, *st)) {
-        const cudaError_t e = launch_decode_mega(m, *st, sc + L.mega, stream);
+        static const int layout = [] {
+            const char* v = getenv("GPTQ_MEGA_LAYOUT");  // development knob: 3 = three consumer groups per SM, 1 = two CTAs per SM
+            return v != nullptr ? atoi(v) : 1;
+        }();
+        cudaError_t e = cudaErrorInvalidConfiguration;
+        if (layout == 3) e = launch_decode_mega3(m, *st, sc + L.mega, stream);
+        if (e == cudaSuccess) return GPTQ_OK;
+        if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
+        e = launch_decode_mega(m, *st, sc + L.mega, stream);
         if (e == cudaSuccess) return GPTQ_OK;
         if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
         // the device cannot co-schedule the persistent grid (or the shape does not fit its staging buffers): per-op kernel chain below
