@@ -1,0 +1,23 @@
+import ctypes, os, sys, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'gptq-for-llama_b200'))
+from gptq_b200 import engine, _lib
+raw = ctypes.CDLL(_lib.LIB_PATH)
+dec = engine.synthetic_llama('7b', max_seq=2048, use_graph=False)
+dec.k_cache.normal_(0, 0.5); dec.v_cache.normal_(0, 0.5)
+dec.positions.fill_(2047); dec.tokens.fill_(1)
+buf = torch.zeros(148 * 64, dtype=torch.int64, device='cuda')
+raw.gptq_debug_set_mega3_trace.argtypes = [ctypes.c_void_p]
+assert raw.gptq_debug_set_mega3_trace(buf.data_ptr()) == 0
+for _ in range(3):
+    dec.step()
+torch.cuda.synchronize()
+t = buf.cpu().view(148, 64).double()
+t0 = t[:, 0].min()
+names = ['Q start', 'Q x staged', 'Q matvec done', 'Q barrier passed', 'A done', 'A barrier passed', 'O done', 'O barrier passed', 'G x staged', 'G done', 'D start(after barrier)', 'D done']
+for l in range(3):
+    print(f'layer {l}: (min / median / max over CTAs, us since kernel start)')
+    for k in range(12):
+        c = (t[:, l * 12 + k] - t0) / 1e3
+        print(f'  {names[k]:24s} {c.min().item():8.2f} {c.median().item():8.2f} {c.max().item():8.2f}')
+

@@ -68,6 +68,63 @@ __global__ void k_lop3(float* out, long long* cyc, int iters) {
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// Mixed streams: do the half-rate pipes overlap?  8 independent HFMA2 chains + 8 independent chains of a second kind per iteration.
+template <int MODE>
+__global__ void k_mix(float* out, long long* cyc, int iters) {
+    __half2 h[8];
+    uint32_t a[8];
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        h[c] = __float2half2_rn((float)threadIdx.x * 1e-3f + c);
+        a[c] = threadIdx.x * 2654435761u + c;
+    }
+    const __half2 m = __float2half2_rn(0.999f), ad = __float2half2_rn(1e-3f);
+    const uint32_t k1 = threadIdx.x | 1u;
+    __syncthreads();
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            if (MODE != 2) h[c] = __hfma2(h[c], m, ad);
+            if (MODE == 0) asm volatile("lop3.b32 %0, %0, %1, 0x64006400, 0x6a;" : "+r"(a[c]) : "r"(k1));
+            if (MODE == 1) asm volatile("add.u32 %0, %0, %1;" : "+r"(a[c]) : "r"(k1));
+            if (MODE == 2) {
+                asm volatile("lop3.b32 %0, %0, %1, 0x64006400, 0x6a;" : "+r"(a[c]) : "r"(k1));
+                asm volatile("shr.u32 %0, %0, 1;" : "+r"(a[(c + 4) & 7]));
+            }
+        }
+        if (MODE == 3) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(acc[c][0]), "+f"(acc[c][1]), "+f"(acc[c][2]), "+f"(acc[c][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]));
+        }
+    }
+    const long long t1 = clock64();
+    float s = acc[0][0] + acc[1][0];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) s += __low2float(h[c]) + (float)a[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <typename K>
+void run_mix(const char* name, K kern, int threads, int iters, float* out, long long* cyc) {
+    kern<<<148, threads>>>(out, cyc, iters);
+    kern<<<148, threads>>>(out, cyc, iters);
+    cudaDeviceSynchronize();
+    long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double avg = 0;
+    for (int i = 0; i < 148; ++i) avg += (double)h[i];
+    avg /= 148;
+    const int wps = threads / 128;
+    printf("MIX %-34s warps/SMSP %d: %.1f cycles per iteration per warp -> %.1f per SMSP per warp-iteration (%s)\n", name, wps, avg / iters, avg / iters / wps,
+           cudaGetErrorString(cudaGetLastError()));
+}
+
 template <typename K>
 void run(const char* name, K kern, int chains, int threads, int iters, float* out, long long* cyc) {
     kern<<<148, threads>>>(out, cyc, iters);
@@ -103,5 +160,10 @@ int main() {
     run("LOP3", k_lop3<1>, 1, 32, it, out, cyc);
     run("LOP3", k_lop3<8>, 8, 32, it, out, cyc);
     run("LOP3", k_lop3<8>, 8, 512, it, out, cyc);
+    run_mix("8 HFMA2 + 8 LOP3", k_mix<0>, 512, it, out, cyc);   // 16 if the pipes overlap, 32 if they serialise
+    run_mix("8 HFMA2 + 8 IADD", k_mix<1>, 512, it, out, cyc);
+    run_mix("8 LOP3 + 8 SHR (both integer)", k_mix<2>, 512, it, out, cyc);
+    run_mix("8 HFMA2 + 2 HMMA", k_mix<3>, 512, it, out, cyc);
+    run_mix("8 HFMA2 + 8 LOP3", k_mix<0>, 128, it, out, cyc);
     return 0;
 }
