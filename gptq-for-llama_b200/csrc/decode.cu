@@ -34,7 +34,7 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = getenv("GPTQ_NO_PDL") == nullptr ? 1 : 0;
+    cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -396,6 +396,11 @@ extern "C" size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int ba
     return scratch_layout(*model, batch, max_seq).total;
 }
 
+extern "C" size_t gptq_llama_persistent_scratch_offset(const gptq_llama_model* model, int batch, int max_seq) {
+    if (model == nullptr || batch < 1 || batch > 8 || max_seq < 1) return 0;
+    return scratch_layout(*model, batch, max_seq).mega;
+}
+
 static bool has_input_perm(const gptq_llama_model& m) {
     for (int l = 0; l < m.n_layers; ++l)
         if (m.layers[l].qkv_perm != nullptr || m.layers[l].o_perm != nullptr || m.layers[l].mlp_perm != nullptr) return true;
@@ -443,15 +448,7 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     uint8_t* sc = reinterpret_cast<uint8_t*>(st->scratch);
     if (mega_supported(m, *st)) {
-        static const int layout = [] {
-            const char* v = getenv("GPTQ_MEGA_LAYOUT");  // development knob: 3 = three consumer groups per SM, 1 = two CTAs per SM
-            return v != nullptr ? atoi(v) : 1;
-        }();
-        cudaError_t e = cudaErrorInvalidConfiguration;
-        if (layout == 3) e = launch_decode_mega3(m, *st, sc + L.mega, stream);
-        if (e == cudaSuccess) return GPTQ_OK;
-        if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
-        e = launch_decode_mega(m, *st, sc + L.mega, stream);
+        const cudaError_t e = launch_decode_mega(m, *st, sc + L.mega, stream);
         if (e == cudaSuccess) return GPTQ_OK;
         if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
         // the device cannot co-schedule the persistent grid (or the shape does not fit its staging buffers): per-op kernel chain below

@@ -1,27 +1,33 @@
-// Persistent decode step: ONE cooperative kernel per token (batch 1, int4, no act-order).
+// Persistent decode step: ONE cooperative kernel per token (batch 1, int4 kernel-form layers).
 //
-// The kernel-chain engine (decode.cu) spends most of a token in per-kernel latencies (parameter fetch, first
-// DRAM round trip, split-K fix-up, launch drain): ~12-23 us per matvec whose weights stream in 1.5-7 us.  Here
-// all 296 CTAs (2 per SM) stay resident for the whole token and walk the same list of operations:
+// One CTA per SM (148 on B200), each with two consumer TEAMS of 8 warps and one producer warp per team.
+// Everything a token reads from HBM -- packed weights with their scales/zeros, the KV cache, the fp16 lm_head --
+// is streamed by the producer warps with cp.async.bulk (the TMA unit) into a per-team ring of 17.1 KB stages in
+// shared memory, in one fixed order per team for the whole token, so the producers run ahead across operations
+// and across grid barriers: while the consumers synchronise, the next operation's bytes are already landing.
 //
 //   per layer:  Q  qkv matvec      x = rmsnorm(resid [+ fp16(acc_down)])           -> RED acc_qkv
-//               A  attention       q,k,v = fp16(acc_qkv); RoPE; KV append; split-KV -> part
+//               A  attention       q,k,v = fp16(acc_qkv); RoPE; KV append; stream-K over 32-key units -> part
 //               O  o_proj matvec   x = combine(part)                                -> RED acc_o
-//               G  gate/up matvec  x = rmsnorm(resid + fp16(acc_o))                 -> RED acc_gate, acc_up
+//               G  gate|up matvec  x = rmsnorm(resid + fp16(acc_o))                 -> RED acc_gate, acc_up
 //               D  down matvec     x = fp16(silu(acc_gate) * acc_up)                -> RED acc_down
 //   then        L  lm_head         x = rmsnorm(resid + fp16(acc_down)), fp16 rows   -> logits;   argmax
 //
-// separated by grid barriers (one atomic + one polled generation word, ~1.5 us).  Split-K partial sums are
-// accumulated with red.global.add.f32 into fp32 vectors that the NEXT operation rounds to fp16 exactly where the
-// reference rounds (a QuantLinear output is fp16), so there is no fix-up pass; each vector is re-zeroed one
-// operation after its last reader.  The weight ring (cp.async, 16 x 512 B per warp, int4_core.cuh) is fed by a
-// producer cursor that runs ahead ACROSS operations: while a CTA waits at a barrier, the next matvec's weights
-// are already in flight, so HBM stays busy through the synchronisation points.
+// Matvec stage = up to 4 k-steps (16 packed rows = 128 k) x 256 columns of ONE quantisation group, plus that
+// group's 256 scales and 256 zeros.  Arithmetic (quant/quant_linear.py:113-133 regrouped): inside a group
+//      sum_k x_k (w_k - z) s  =  s * ( sum_k x_k w_k  -  z * sum_k x_k )
+// so the consumers feed the RAW nibbles to the tensor pipe (mma.sync m16n8k16, operands swapped: A = 16 output
+// columns x 16 k of weights, B = x): a nibble masked in place IS an fp16 subnormal (n * 2^-24, or 16 n * 2^-24 for
+// the odd nibbles, whose x is pre-scaled by 1/16 when it is staged), products and the fp32 accumulation are
+// exact, and scale / zero are applied ONCE per group on the fp32 accumulator together with the group's sum of
+// x (computed when x is staged).  5 integer instructions + 1 HMMA per packed word; the result differs from the
+// reference only by NOT rounding every dequantised weight to fp16 (it is closer to the exact product); the
+// 1e-3 tests in tests/ hold it to the oracle.  -DGPTQ_DQ_EXACT_INT selects the variant that converts nibbles to
+// exact fp16 integers (magic-number trick, 4 more fp16 instructions per word) and leaves x unscaled.
 //
-// Arithmetic per element is the same as in qmatvec.cu / decode.cu (reference-exact dequant, fp32 accumulate);
-// only the fp32 summation order of the <= 20 split-K partials is unordered (atomics).
-#include <cstdlib>
-
+// Split-K partial sums are accumulated with red.global.add.f32 into fp32 vectors that the NEXT operation
+// rounds to fp16 exactly where the reference rounds (a QuantLinear output is fp16); each vector is re-zeroed
+// one operation after its last reader.  Only the fp32 summation order of those partials is unordered.
 #include "common.cuh"
 #include "int4_core.cuh"
 #include "kernels.h"
@@ -31,23 +37,32 @@ namespace {
 
 using namespace int4;
 
-constexpr int kWarps = 8;
-constexpr int kThreads = 256;
+constexpr int kTeams = 2;                             // consumer teams per CTA
+constexpr int kTeamWarps = 8;
+constexpr int kTeamThreads = kTeamWarps * 32;         // 256
+constexpr int kConsumers = kTeams * kTeamThreads;     // 512
+constexpr int kConsumerWarps = kTeams * kTeamWarps;   // 16
+constexpr int kBlock = kConsumers + 32 * kTeams;      // + one producer warp per team
 constexpr int kSlabCols = 256;
-constexpr int kProducers = 2;                      // producer warps: tile i is fetched by producer i % kProducers
-constexpr int kBlock = kThreads + 32 * kProducers;  // 8 consumer warps + the producer warps
-constexpr int kRowPitch = 1024 + 32;   // smem pitch of a 1 KB weight row: +32 B makes the 4 rows of a k-step hit distinct bank groups
-constexpr int kTile = 4 * kRowPitch;   // one ring stage: 4 packed rows x 256 columns of one matrix (4 KB of weights)
-constexpr int kStages = 15;            // 15 x 4224 B = 63,360 B of weights in flight per CTA
+constexpr int kRowPitch = 1024 + 32;   // smem pitch of a 1 KB weight row: +32 B puts the 4 rows of a k-step on distinct bank groups
+constexpr int kStageSteps = 4;         // k-steps (of 32 k = 4 packed rows) per stage
+constexpr int kScaleOff = kStageSteps * 4 * kRowPitch;  // 16896: 256 fp16 scales of the stage's group
+constexpr int kZeroOff = kScaleOff + 512;               // 17408: 32 qzeros words (256 nibbles)
+constexpr int kStageBytes = kZeroOff + 128;             // 17536
 constexpr int kHD = 128;
-constexpr int kAttnChunk = 256;  // keys per attention work item (two passes of 128 with an online-softmax merge)
-constexpr int kAttnPass = 128;
-constexpr int kRec = kHD + 4;     // floats per split-KV partial record: m, l, 2 pad, o[128] (keeps o 16-byte aligned)
+constexpr int kKeysPerUnit = 32;       // attention work unit: 32 keys of one head = 8 KB of K + 8 KB of V = one stage
+constexpr int kVOff = 8192 + 256;      // V rows of a KV stage (K rows at offset 0)
+constexpr int kRec = kHD + 4;          // floats per attention partial record: m, l, 2 pad, o[128]
 constexpr int kMaxLayers = 80;
-#ifndef GPTQ_STEP_UNROLL
-#define GPTQ_STEP_UNROLL 2
+constexpr int kMaxStages = 8;
+constexpr int kTeamScratch = 5632;     // per-team scratch (attention merge buffers / lm_head partials)
+constexpr int kLmStageBytes = 16384;   // lm_head bytes per stage (whole rows)
+
+#ifdef GPTQ_DQ_EXACT_INT
+constexpr bool kSubnormal = false;
+#else
+constexpr bool kSubnormal = true;
 #endif
-constexpr int kStepUnroll = GPTQ_STEP_UNROLL;  // unroll factor of the per-tile loop (development knob)
 
 #ifdef GPTQ_TRACE
 }  // namespace
@@ -72,6 +87,7 @@ struct MatDesc {
     const uint32_t* qw;
     const __half* sc;
     const uint32_t* qz;
+    int gs_steps;  // k-steps per quantisation group (groupsize / 32)
 };
 struct LayerDesc {
     MatDesc qkv, o, gate, up, down;
@@ -82,7 +98,7 @@ struct LayerDesc {
     const int32_t* mlp_perm;
 };
 struct MegaParams {
-    int n_layers, H, I, V, n_heads, groupsize, max_seq, nsplit;
+    int n_layers, H, I, V, n_heads, max_seq, n_stages, lm_rows;
     float eps, inv_base, scale;
     const __half* embed;
     const __half* final_norm;
@@ -101,101 +117,172 @@ struct MegaParams {
     float* acc_g;      // [I]
     float* acc_u;      // [I]
     float* acc_d;      // [H]
-    float* part;       // [heads][nsplit][130]
+    float* part;       // [teams][2][kRec]
     float* rope_cs;    // [128]: cos[64], sin[64] of this step's position
-    unsigned long long* bar;  // monotonic arrival counter of the grid barrier
+    unsigned long long* bar;  // [0]: monotonic arrival counter of the grid barrier, [1]: its value when the previous launch ended
     LayerDesc layers[kMaxLayers];
 };
 
-// One matvec of the op list, as the weight producer sees it.
-struct MatOp {
-    const uint32_t* qw[2];
-    int K, N, ntiles_per_step;  // 2 for the fused gate/up
-};
+// ---- work split ------------------------------------------------------------------------------------------------
+// U units of an operation are dealt to the nb teams as contiguous ranges [T*U/nb, (T+1)*U/nb).
+__device__ __forceinline__ void team_range(unsigned T, unsigned U, unsigned nb, int& a, int& b) {
+    a = (int)((T * U) / nb);  // T * U < 2^32 (checked by mega_plan)
+    b = (int)(((T + 1) * U) / nb);
+}
+// k-steps of the stage that starts at step ks of a segment with `left` steps to go
+__device__ __forceinline__ int stage_steps(int ks, int gs_steps, int left) { return min(min(kStageSteps, gs_steps - ks % gs_steps), left); }
 
-__device__ __forceinline__ MatOp mat_op(const MegaParams& p, int idx) {
-    // matvec ops in execution order: 4 per layer (qkv, o, gate|up, down)
-    const LayerDesc& L = p.layers[idx >> 2];
-    MatOp m;
-    m.ntiles_per_step = 1;
-    m.qw[1] = nullptr;
-    switch (idx & 3) {
-        case 0: m.qw[0] = L.qkv.qw; m.K = p.H; m.N = 3 * p.H; break;
-        case 1: m.qw[0] = L.o.qw; m.K = p.H; m.N = p.H; break;
-        case 2: m.qw[0] = L.gate.qw; m.qw[1] = L.up.qw; m.K = p.H; m.N = p.I; m.ntiles_per_step = 2; break;
-        default: m.qw[0] = L.down.qw; m.K = p.I; m.N = p.H; break;
+// position of this step, clamped to the cache (the host rejects pos >= max_seq; the kernel must not write outside)
+__device__ __forceinline__ int step_pos(const MegaParams& p) { return min(max(p.positions[0], 0), p.max_seq - 1); }
+
+// ---- team / CTA synchronisation ------------------------------------------------------------------------------------
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, 256;" ::"r"(team + 1) : "memory"); }
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 3, 512;" ::: "memory"); }  // all consumer warps (not the producers)
+
+// ---- producer ------------------------------------------------------------------------------------------------------
+struct ProdRing {
+    uint32_t ring, full, empty;
+    int stage, use, nstages;
+};
+__device__ __forceinline__ uint32_t prod_acquire(ProdRing& r, uint32_t& bar) {
+    if (r.use > 0) mbar_wait_backoff(r.empty + r.stage * 8, (r.use - 1) & 1u);  // the consumers released the previous use of this stage
+    bar = r.full + r.stage * 8;
+    return r.ring + r.stage * kStageBytes;
+}
+__device__ __forceinline__ void prod_advance(ProdRing& r) {
+    if (++r.stage == r.nstages) {
+        r.stage = 0;
+        ++r.use;
     }
-    return m;
 }
 
-// ---- pipeline state --------------------------------------------------------------------------------------
-// A dedicated producer warp streams 4 KB tiles (4 packed rows x 1 KB: whole DRAM-page-sized row segments, one
-// cp.async.bulk each) into a 15-stage ring shared by the CTA; the 8 consumer warps each read their 32-column
-// stripe of every tile.  full[s]: producer -> consumers (expect_tx 4096 B); empty[s]: 8 consumer warps -> producer.
-// The producer walks the matvec list of the whole token on its own, so it runs ahead across grid barriers.
-struct Pipe {
-    uint32_t ring;   // smem address of stage 0
-    uint32_t full;   // smem address of full[0]  (8 B each; empty[s] sits kStages * 8 bytes after full[s])
-    uint32_t empty;  // smem address of empty[0]
-    // consumer cursors (per thread): stages are consumed in strict rotation, so one parity bit per round suffices
-    uint32_t tile;    // smem address of this lane's 16 B in the current stage
-    uint32_t bar;     // smem address of full[current stage]
-    uint32_t parity;  // expected parity of the current round
-    int left;         // stages until the ring wraps
-};
+// weights of one matvec (NM matrices side by side: gate|up is one virtual matrix of 2 * N/256 slabs)
+template <int NM>
+__device__ void produce_matvec(ProdRing& r, const MatDesc* const (&md)[NM], int K, int N, unsigned T, unsigned nb) {
+    const int nk = K / 32, nslab = N / kSlabCols;
+    int u, u1;
+    team_range(T, (unsigned)(NM * nslab) * nk, nb, u, u1);
+    const size_t row_bytes = (size_t)N * 4;
+#pragma unroll 1
+    while (u < u1) {
+        const int slab_v = u / nk;
+        int ks = u - slab_v * nk;
+        const int nseg = min(nk - ks, u1 - u);
+        const int mi = (NM > 1 && slab_v >= nslab) ? 1 : 0;
+        const int slab = slab_v - mi * nslab;
+        const MatDesc& m = *md[mi];
+        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(m.qw) + (size_t)slab * (kSlabCols * 4);
+        int left = nseg;
+#pragma unroll 1
+        while (left > 0) {
+            const int n = stage_steps(ks, m.gs_steps, left);
+            uint32_t bar;
+            const uint32_t dst = prod_acquire(r, bar);
+            mbar_expect_tx(bar, n * 4096 + 640);
+            const uint8_t* src = wbase + (size_t)(ks * 4) * row_bytes;
+#pragma unroll 4
+            for (int rr = 0; rr < 4 * n; ++rr) bulk_copy_g2s(dst + rr * kRowPitch, src + rr * row_bytes, 1024, bar);
+            const int g = ks / m.gs_steps;
+            bulk_copy_g2s(dst + kScaleOff, m.sc + (size_t)g * N + slab * kSlabCols, 512, bar);
+            bulk_copy_g2s(dst + kZeroOff, m.qz + (size_t)g * (N >> 3) + slab * (kSlabCols / 8), 128, bar);
+            prod_advance(r);
+            ks += n;
+            left -= n;
+        }
+        u += nseg;
+    }
+}
 
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }  // the 8 consumer warps only
+__device__ void produce_kv(ProdRing& r, const MegaParams& p, int layer, unsigned T, unsigned nb) {
+    const int Tlen = step_pos(p) + 1;
+    const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
+    int u, u1;
+    team_range(T, (unsigned)(p.n_heads * upb), nb, u, u1);
+    const __half* kc = p.k_cache + layer * p.layer_stride;
+    const __half* vc = p.v_cache + layer * p.layer_stride;
+#pragma unroll 1
+    for (; u < u1; ++u) {
+        const int head = u / upb, b = u - head * upb;
+        const int nrows = min(kKeysPerUnit, Tlen - b * kKeysPerUnit);
+        const size_t off = ((size_t)head * p.max_seq + (size_t)b * kKeysPerUnit) * kHD;
+        uint32_t bar;
+        const uint32_t dst = prod_acquire(r, bar);
+        mbar_expect_tx(bar, nrows * 512);
+        bulk_copy_g2s(dst, kc + off, nrows * 256, bar);
+        bulk_copy_g2s(dst + kVOff, vc + off, nrows * 256, bar);
+        prod_advance(r);
+    }
+}
 
-__device__ void producer_loop(const MegaParams& p, uint32_t ring, uint32_t full, uint32_t empty, int pw) {
-    int stage = 0, use = 0, mine = 0;  // ring position / use count of the next tile; mine: tiles until this producer's turn
-    mine = pw;
-    const int n_ops = p.n_layers * 4;
+__device__ void produce_lm_head(ProdRing& r, const MegaParams& p, unsigned T, unsigned nb) {
+    const int R = p.lm_rows;
+    int u, u1;
+    team_range(T, (unsigned)((p.V + R - 1) / R), nb, u, u1);
 #pragma unroll 1
-    for (int op = 0; op < n_ops; ++op) {
-        const MatOp m = mat_op(p, op);
-        const unsigned nk = m.K / 32, U = (unsigned)(m.N / kSlabCols) * nk, nb = gridDim.x;
-        const int u0 = (int)((blockIdx.x * U) / nb), u1 = (int)(((blockIdx.x + 1) * U) / nb);
-        if (u1 <= u0) continue;
-        const int slab0 = u0 / nk;
-        int ks = u0 - slab0 * nk;
-        const size_t row_bytes = (size_t)m.N * 4;
-        const uint8_t* src[2];
-        src[0] = reinterpret_cast<const uint8_t*>(m.qw[0]) + (size_t)(ks * 4) * row_bytes + (size_t)slab0 * (kSlabCols * 4);
-        src[1] = m.qw[1] ? reinterpret_cast<const uint8_t*>(m.qw[1]) + (size_t)(ks * 4) * row_bytes + (size_t)slab0 * (kSlabCols * 4) : nullptr;
-        const long long wrap = (long long)(kSlabCols * 4) - (long long)nk * 4 * (long long)row_bytes;  // next slab, back to packed row 0
+    for (; u < u1; ++u) {
+        const int nrows = min(R, p.V - u * R);
+        uint32_t bar;
+        const uint32_t dst = prod_acquire(r, bar);
+        const uint32_t bytes = (uint32_t)nrows * p.H * 2;
+        mbar_expect_tx(bar, bytes);
+        bulk_copy_g2s(dst, p.lm_head + (size_t)u * R * p.H, bytes, bar);
+        prod_advance(r);
+    }
+}
+
+__device__ void producer_loop(const MegaParams& p, ProdRing r, unsigned T, unsigned nb) {
 #pragma unroll 1
-        for (int u = u0; u < u1; ++u) {
-#pragma unroll 1
-            for (int w = 0; w < m.ntiles_per_step; ++w) {
-                if (mine == 0) {
-                    if (use > 0) mbar_wait(empty + stage * 8, (use - 1) & 1u);  // consumers released the previous use of this stage
-                    const uint32_t bar = full + stage * 8;
-                    const uint32_t dst = ring + stage * kTile;
-                    mbar_expect_tx(bar, 4096);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) bulk_copy_g2s(dst + r * kRowPitch, src[w] + r * row_bytes, 1024, bar);
-                    mine = kProducers;
-                }
-                --mine;
-                if (++stage == kStages) {
-                    stage = 0;
-                    ++use;
-                }
-            }
-            src[0] += 4 * row_bytes;
-            if (src[1]) src[1] += 4 * row_bytes;
-            if (++ks == (int)nk) {
-                ks = 0;
-                src[0] += wrap;
-                if (src[1]) src[1] += wrap;
-            }
+    for (int l = 0; l < p.n_layers; ++l) {
+        const LayerDesc& L = p.layers[l];
+        {
+            const MatDesc* const md[1] = {&L.qkv};
+            produce_matvec<1>(r, md, p.H, 3 * p.H, T, nb);
+        }
+        produce_kv(r, p, l, T, nb);
+        {
+            const MatDesc* const md[1] = {&L.o};
+            produce_matvec<1>(r, md, p.H, p.H, T, nb);
+        }
+        {
+            const MatDesc* const md[2] = {&L.gate, &L.up};
+            produce_matvec<2>(r, md, p.H, p.I, T, nb);
+        }
+        {
+            const MatDesc* const md[1] = {&L.down};
+            produce_matvec<1>(r, md, p.I, p.H, T, nb);
         }
     }
+    produce_lm_head(r, p, T, nb);
 }
 
-// ---- grid barrier: one monotonic 64-bit arrival counter (never reset: every launch adds a multiple of gridDim.x) ----
+// ---- consumer side of the ring -----------------------------------------------------------------------------------------
+struct ConsRing {
+    uint32_t ring, full;  // stage 0 / full[0]; empty[s] sits kMaxStages * 8 bytes after full[s]
+    uint32_t tile, bar;   // current stage
+    uint32_t parity;
+    int left, nstages;
+};
+__device__ __forceinline__ uint32_t cons_wait(const ConsRing& c) {
+    mbar_wait(c.bar, c.parity);
+    return c.tile;
+}
+// every lane of the warp has finished reading the stage
+__device__ __forceinline__ void cons_release(ConsRing& c, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(c.bar + kMaxStages * 8);
+    c.tile += kStageBytes;
+    c.bar += 8;
+    if (--c.left == 0) {
+        c.left = c.nstages;
+        c.tile = c.ring;
+        c.bar = c.full;
+        c.parity ^= 1u;
+    }
+}
+
+// ---- grid barrier: one monotonic 64-bit arrival counter ----------------------------------------------------------------
 // arrive = red.release (fire and forget), wait = poll the same word with ld.acquire until it reaches this barrier's
-// target: about 1.5 L2 round trips.  `target` lives in thread 0 of each CTA.
+// target.  `target` lives in thread 0 of each CTA.
 __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned long long& target) {
     cta_sync();
     if (threadIdx.x == 0) {
@@ -214,7 +301,7 @@ __device__ __forceinline__ void zero_slice(float* buf, int n) {
     // this CTA's share of a distributed memset (n is a multiple of 4)
     const int per = ((n / 4 + gridDim.x - 1) / gridDim.x);
     const int lo = blockIdx.x * per, hi = min(n / 4, lo + per);
-    for (int i = lo + threadIdx.x; i < hi; i += kThreads) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = lo + threadIdx.x; i < hi; i += kConsumers) reinterpret_cast<float4*>(buf)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 __device__ __forceinline__ float block_sum(float v, float* red_s) {
@@ -224,464 +311,623 @@ __device__ __forceinline__ float block_sum(float v, float* red_s) {
     cta_sync();
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) t += red_s[w];
+    for (int w = 0; w < kConsumerWarps; ++w) t += red_s[w];
     return t;
 }
 
-// store 8 consecutive k (natural order, as 4 half2 words) k-permuted: (k0,k4)(k1,k5)(k2,k6)(k3,k7)
-__device__ __forceinline__ void store_perm8(__half* dst, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+// ---- x staging ----------------------------------------------------------------------------------------------------------
+// Matvec input layout: 8 consecutive k (natural order, 4 half2 words w0..w3) are stored k-permuted as
+// (k0,k4)(k1,k5)(k2,k6)(k3,k7): the B fragments of the two MMAs of a packed word; the pairs that meet the ODD
+// nibbles (k1,k5 / k3,k7; mask 0x00f000f0 = 16 n) are pre-scaled by 1/16 (kSubnormal only).
+__device__ __forceinline__ uint4 perm8(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     uint4 o;
     o.x = __byte_perm(w0, w2, 0x5410);
     o.y = __byte_perm(w0, w2, 0x7632);
     o.z = __byte_perm(w1, w3, 0x5410);
     o.w = __byte_perm(w1, w3, 0x7632);
-    *reinterpret_cast<uint4*>(dst) = o;
+    if (kSubnormal) {
+        const __half2 sixteenth = __float2half2_rn(0.0625f);
+        o.y = h2_as_u32(__hmul2(u32_as_h2(o.y), sixteenth));
+        o.w = h2_as_u32(__hmul2(u32_as_h2(o.w), sixteenth));
+    }
+    return o;
+}
+// position of natural index j (0..7) inside the permuted run of 8, and whether it is pre-scaled
+__device__ __forceinline__ int perm_pos(int j) { return ((j & 3) << 1) + (j >> 2); }
+__device__ __forceinline__ bool perm_scaled(int j) { return kSubnormal && (j & 1); }
+
+// sum of the EFFECTIVE x of one staged run of 8 (what the tensor pipe will multiply the nibbles with)
+__device__ __forceinline__ float run_sum(uint4 v) {
+    const float2 a = __half22float2(u32_as_h2(v.x)), b = __half22float2(u32_as_h2(v.y)), c = __half22float2(u32_as_h2(v.z)), d = __half22float2(u32_as_h2(v.w));
+    const float even = (a.x + a.y) + (c.x + c.y), odd = (b.x + b.y) + (d.x + d.y);
+    return kSubnormal ? fmaf(odd, 16.0f, even) : even + odd;
+}
+// xsum[s] = sum over the 32 k of step s of the staged x (4 runs of 8), for s < nsteps; `nthreads` threads (a multiple of 32) cooperate
+__device__ __forceinline__ void compute_xsum(const __half* xs, int nsteps, float* xsum, int tid, int nthreads) {
+    const int n4 = nsteps * 4;
+    for (int base = 0; base < n4; base += nthreads) {
+        const int idx = base + tid;
+        float v = 0.f;
+        if (idx < n4) v = run_sum(*reinterpret_cast<const uint4*>(xs + idx * 8));
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (idx < n4 && (idx & 3) == 0) xsum[idx >> 2] = v;
+    }
 }
 
-// x = rmsnorm(src [+ fp16(acc)]) for the whole row (K = H), staged k-permuted in xs; the updated residual stream
-// (src + fp16(acc)) is written to resid_out by slices.  src/acc/resid_out are global.
-// ACT: the matvec's packed rows were regrouped by the host (act-order): position k' of xs holds feature perm[k'].
-template <bool ACT>
-__device__ void stage_norm(const MegaParams& p, const __half* src, const float* acc, const __half* norm_w, __half* resid_out, __half* xs, __half* tmp,
-                           float* red_s, const int32_t* perm) {
-    const int H = p.H, tid = threadIdx.x;
+// x = rmsnorm(src [+ fp16(acc)]) for the whole row (K = H), staged in xs (matvec layout, or natural order if PLAIN)
+// with its per-step sums in xsum; the updated residual stream (src + fp16(acc)) is written to resid_out by slices.
+// All 512 consumer threads.  ACT: the matvec's packed rows were regrouped by the host: position k' holds feature perm[k'].
+template <bool ACT, bool PLAIN>
+__device__ void stage_norm(const MegaParams& p, const __half* src, const float* acc, const __half* norm_w, __half* resid_out, __half* xs, float* xsum,
+                           __half* tmp, float* red_s, const int32_t* perm) {
+    const int H = p.H, tid = threadIdx.x, nch = H / 8;
     float ss = 0.f;
-    for (int c = tid; c < H / 8; c += kThreads) {
-        const uint4 v = *reinterpret_cast<const uint4*>(src + c * 8);
-        uint32_t xv[4] = {v.x, v.y, v.z, v.w};
-        if (acc != nullptr) {
-            const float4 a0 = *reinterpret_cast<const float4*>(acc + c * 8), a1 = *reinterpret_cast<const float4*>(acc + c * 8 + 4);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    uint4 nwv[2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)  // residual + fp16(linear output): an fp16 add, as in HF's decoder layer
-                xv[j] = h2_as_u32(__hadd2(u32_as_h2(xv[j]), __floats2half2_rn(av[2 * j], av[2 * j + 1])));
-        }
+    for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kConsumers;
+        nwv[i] = make_uint4(0, 0, 0, 0);
+        if (c < nch) {
+            nwv[i] = *reinterpret_cast<const uint4*>(norm_w + c * 8);  // same round trip as src / acc
+            const uint4 v = ld_cg_u4(src + c * 8);  // written by other CTAs (residual slices): L2, not this SM's L1
+            uint32_t xv[4] = {v.x, v.y, v.z, v.w};
+            if (acc != nullptr) {
+                const float4 a0 = ld_cg4(acc + c * 8), a1 = ld_cg4(acc + c * 8 + 4);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(u32_as_h2(xv[j]));
-            ss = fmaf(f.x, f.x, ss);
-            ss = fmaf(f.y, f.y, ss);
+                for (int j = 0; j < 4; ++j)  // residual + fp16(linear output): an fp16 add, as in HF's decoder layer
+                    xv[j] = h2_as_u32(__hadd2(u32_as_h2(xv[j]), __floats2half2_rn(av[2 * j], av[2 * j + 1])));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __half22float2(u32_as_h2(xv[j]));
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
+            }
+            *reinterpret_cast<uint4*>(tmp + c * 8) = make_uint4(xv[0], xv[1], xv[2], xv[3]);
         }
-        *reinterpret_cast<uint4*>(tmp + c * 8) = make_uint4(xv[0], xv[1], xv[2], xv[3]);
     }
-    const float tot = block_sum(ss, red_s);
+    const float tot = block_sum(ss, red_s);  // its barriers also publish tmp
     const float rstd = 1.0f / sqrtf(tot / (float)H + p.eps);
-    const int per = (H / 8 + gridDim.x - 1) / gridDim.x;
-    const int wlo = blockIdx.x * per, whi = min(H / 8, wlo + per);
-    if constexpr (ACT) {
-        if (perm != nullptr) {
-            // norm_w is given in regrouped order (gptq_b200.h): the index vector and the weights travel together, the gather
-            // itself reads shared memory
-            for (int c = tid; c < H / 8; c += kThreads) {
-                if (resid_out != nullptr && c >= wlo && c < whi) *reinterpret_cast<uint4*>(resid_out + c * 8) = *reinterpret_cast<const uint4*>(tmp + c * 8);
-                const ::int4 p0 = *reinterpret_cast<const ::int4*>(perm + c * 8), p1 = *reinterpret_cast<const ::int4*>(perm + c * 8 + 4);
-                const uint4 nw = *reinterpret_cast<const uint4*>(norm_w + c * 8);
-                const int k[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-                const uint32_t wv[4] = {nw.x, nw.y, nw.z, nw.w};
-                uint32_t o[4];
+    if (resid_out != nullptr) {
+        const int per = (nch + gridDim.x - 1) / gridDim.x;
+        const int c = blockIdx.x * per + tid;
+        if (tid < per && c < nch) *reinterpret_cast<uint4*>(resid_out + c * 8) = *reinterpret_cast<const uint4*>(tmp + c * 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int c = tid + i * kConsumers;
+        if (c < nch) {
+            float xf[8];
+            bool gathered = false;
+            if constexpr (ACT) {
+                if (perm != nullptr) {  // norm_w is given in regrouped order (gptq_b200.h); the gather itself reads shared memory
+                    const ::int4 p0 = *reinterpret_cast<const ::int4*>(perm + c * 8), p1 = *reinterpret_cast<const ::int4*>(perm + c * 8 + 4);
+                    const int k[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) xf[j] = __half2float(tmp[k[j]]);
+                    gathered = true;
+                }
+            }
+            if (!gathered) {
+                const uint4 v = *reinterpret_cast<const uint4*>(tmp + c * 8);
+                const uint32_t xv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const float2 wf = __half22float2(u32_as_h2(wv[j]));
-                    const float x0 = __half2float(tmp[k[2 * j]]), x1 = __half2float(tmp[k[2 * j + 1]]);
-                    o[j] = h2_as_u32(__floats2half2_rn(__fmul_rn(__fmul_rn(x0, rstd), wf.x), __fmul_rn(__fmul_rn(x1, rstd), wf.y)));
+                    const float2 f = __half22float2(u32_as_h2(xv[j]));
+                    xf[2 * j] = f.x;
+                    xf[2 * j + 1] = f.y;
                 }
-                store_perm8(xs + c * 8, o[0], o[1], o[2], o[3]);
             }
-            return;
-        }
-    }
-    for (int c = tid; c < H / 8; c += kThreads) {
-        const uint4 v = *reinterpret_cast<const uint4*>(tmp + c * 8);
-        if (resid_out != nullptr && c >= wlo && c < whi) *reinterpret_cast<uint4*>(resid_out + c * 8) = v;
-        const uint4 nw = *reinterpret_cast<const uint4*>(norm_w + c * 8);
-        const uint32_t xv[4] = {v.x, v.y, v.z, v.w}, wv[4] = {nw.x, nw.y, nw.z, nw.w};
-        uint32_t o[4];
+            const uint32_t wv[4] = {nwv[i].x, nwv[i].y, nwv[i].z, nwv[i].w};
+            uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float2 xf = __half22float2(u32_as_h2(xv[j])), wf = __half22float2(u32_as_h2(wv[j]));
-            o[j] = h2_as_u32(__floats2half2_rn(__fmul_rn(__fmul_rn(xf.x, rstd), wf.x), __fmul_rn(__fmul_rn(xf.y, rstd), wf.y)));
+            for (int j = 0; j < 4; ++j) {  // fp32 normalise, fp32 weight multiply, one rounding to fp16 (quant/triton_norm.py:30-38)
+                const float2 wf = __half22float2(u32_as_h2(wv[j]));
+                o[j] = h2_as_u32(__floats2half2_rn(__fmul_rn(__fmul_rn(xf[2 * j], rstd), wf.x), __fmul_rn(__fmul_rn(xf[2 * j + 1], rstd), wf.y)));
+            }
+            *reinterpret_cast<uint4*>(xs + c * 8) = PLAIN ? make_uint4(o[0], o[1], o[2], o[3]) : perm8(o[0], o[1], o[2], o[3]);
         }
-        store_perm8(xs + c * 8, o[0], o[1], o[2], o[3]);
     }
+    cta_sync();
+    if constexpr (!PLAIN) {
+        compute_xsum(xs, H / 32, xsum, tid, kConsumers);
+        cta_sync();
+    }
+}
+
+// ---- matvec consumer ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_16816_z(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+                 : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(0.f));
+}
+
+// the four A registers (k-pairs (0,4), (1,5), (2,6), (3,7)) of one packed word
+__device__ __forceinline__ void nibble_regs(uint32_t q, uint32_t (&a)[4]) {
+    const uint32_t q8 = q >> 8;
+    if (kSubnormal) {  // masked in place: fp16 subnormals n * 2^-24 and 16 n * 2^-24
+        a[0] = q & 0x000f000fu;
+        a[1] = q & 0x00f000f0u;
+        a[2] = q8 & 0x000f000fu;
+        a[3] = q8 & 0x00f000f0u;
+    } else {  // exact fp16 integers: (1024 + n) - 1024 and (1024 + 16 n) / 16 - 64
+        const __half2 c1024 = __float2half2_rn(1024.0f), sixteenth = __float2half2_rn(0.0625f), m64 = __float2half2_rn(-64.0f);
+        a[0] = h2_as_u32(__hsub2(nibbles_to_h2<0x000f000fu>(q), c1024));
+        a[1] = h2_as_u32(__hfma2(nibbles_to_h2<0x00f000f0u>(q), sixteenth, m64));
+        a[2] = h2_as_u32(__hsub2(nibbles_to_h2<0x000f000fu>(q8), c1024));
+        a[3] = h2_as_u32(__hfma2(nibbles_to_h2<0x00f000f0u>(q8), sixteenth, m64));
+    }
+}
+
+// one k-step (4 packed words of this lane = columns 4g..4g+3 x 8 k) into the two accumulators
+template <bool FIRST>
+__device__ __forceinline__ void step_mma(const uint4& q, const uint4& xf, float (&acc0)[4], float (&acc1)[4]) {
+    uint32_t c0[4], c1[4], c2[4], c3[4];
+    nibble_regs(q.x, c0);
+    nibble_regs(q.y, c1);
+    nibble_regs(q.z, c2);
+    nibble_regs(q.w, c3);
+    if (FIRST) {
+        mma_16816_z(acc0, c0[0], c1[0], c0[1], c1[1], xf.x, xf.y);
+        mma_16816_z(acc1, c2[0], c3[0], c2[1], c3[1], xf.x, xf.y);
+    } else {
+        mma_16816(acc0, c0[0], c1[0], c0[1], c1[1], xf.x, xf.y);
+        mma_16816(acc1, c2[0], c3[0], c2[1], c3[1], xf.x, xf.y);
+    }
+    mma_16816(acc0, c0[2], c1[2], c0[3], c1[3], xf.z, xf.w);
+    mma_16816(acc1, c2[2], c3[2], c2[3], c3[3], xf.z, xf.w);
 }
 
 enum XMode { X_FULL = 0, X_ATTN = 1, X_SWIGLU = 2 };
 
-// One matvec op for this CTA: consume the tiles of its unit range from the ring, RED the results.
-// xs holds either the full K row (X_FULL, staged by stage_norm before the call) or is (re)staged per segment here.
-template <bool DUAL, int XMODE, bool ACT = false>
-__device__ void run_matvec(const MegaParams& p, Pipe& pipe, const MatDesc& w0, const MatDesc& w1, int K, int N,
-                           float* out0, float* out1, __half* xs, const int32_t* perm = nullptr) {
-    constexpr int NW = DUAL ? 2 : 1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const unsigned nk = K / 32, U = (unsigned)(N / kSlabCols) * nk, nb = gridDim.x;
-    const int u_begin = (int)((blockIdx.x * U) / nb), u_end = (int)(((blockIdx.x + 1) * U) / nb);
-    const int gs_steps = p.groupsize >> 5;
-    const MatDesc* wd[2] = {&w0, &w1};
+struct TeamCtx {
+    int team, wt, lane, ttid;  // team, warp in team, lane, thread in team
+    unsigned T, nb;            // global team index / number of teams
+    __half* xseg;              // this team's half of the xs buffer (per-segment inputs of O and D)
+    float* xsum_seg;
+    uint8_t* scratch;          // kTeamScratch bytes
+};
 
-#ifdef GPTQ_TRACE
-    long long wait_cycles = 0;
-    const long long tm0 = clock64();
-#endif
-    int u = u_begin;
+// One matvec op for this team: consume the stages of its unit range from the ring, RED the results.
+// NM = 2: gate|up as one virtual matrix (out0 = gate accumulators, out1 = up accumulators).
+template <int NM, int XMODE, bool ACT = false>
+__device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, int gs_steps, int K, int N, float* out0, float* out1, const __half* xs_full,
+                           const float* xsum_full, const int32_t* perm = nullptr) {
+    const int lane = tc.lane, g = lane >> 2, t = lane & 3;
+    const int nk = K / 32, nslab = N / kSlabCols;
+    int u, u_end;
+    team_range(tc.T, (unsigned)(NM * nslab) * nk, tc.nb, u, u_end);
+    const uint32_t lane_w = (uint32_t)(t * kRowPitch + tc.wt * 128 + g * 16);     // this lane's 16 B in row t of a k-step
+    const uint32_t lane_s = (uint32_t)(kScaleOff + (tc.wt * 32 + 4 * g) * 2);      // its 4 scales
+    const uint32_t lane_z = (uint32_t)(kZeroOff + (tc.wt * 4 + (g >> 1)) * 4);     // the qzeros word holding its 4 zeros
+    const int zshift = (g & 1) * 16;
+    const float unit = kSubnormal ? 16777216.0f : 1.0f;  // the accumulators are in units of 2^-24
+
 #pragma unroll 1
     while (u < u_end) {
-        const int slab = u / nk;
-        const int ks0 = u - slab * nk;
-        const int nsteps = min((int)nk - ks0, u_end - u);
-        const int col = slab * kSlabCols + warp * 32 + 4 * g;
-        const int zshift = (col & 4) * 4;
-
-        GroupRaw raw[NW];
-        GroupConst gc[NW];
-        const __half* scp[NW];
-        const uint32_t* qzp[NW];
-        {
-            const int grp0 = (ks0 * 32) / p.groupsize;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                scp[w] = wd[w]->sc + (size_t)grp0 * N + col;
-                qzp[w] = wd[w]->qz + (size_t)grp0 * (N >> 3) + (col >> 3);
-                raw[w] = load_group_raw(scp[w], qzp[w]);
-                scp[w] += N;
-                qzp[w] += N >> 3;
-            }
-        }
+        const int slab_v = u / nk;
+        const int ks0 = u - slab_v * nk;
+        const int nseg = min(nk - ks0, u_end - u);
+        const int mi = (NM > 1 && slab_v >= nslab) ? 1 : 0;
+        float* outp = (mi ? out1 : out0) + (slab_v - mi * nslab) * kSlabCols + tc.wt * 32 + 4 * g;
 
         uint32_t xaddr;
+        const float* xsum;
         if constexpr (XMODE == X_FULL) {
-            xaddr = smem_u32(xs) + (ks0 * 32 + t * 8) * 2;
+            xaddr = smem_u32(xs_full) + (ks0 * 32 + t * 8) * 2;
+            xsum = xsum_full + ks0;
         } else {
-            // stage this segment's k-range [ks0*32, (ks0+nsteps)*32) of the op input
-            cta_sync();  // previous readers of xs are done
+            // stage this segment's k-range [ks0*32, (ks0+nseg)*32) of the op input into the team's buffer
+            team_sync(tc.team);  // previous readers of xseg are done
             const int kbeg = ks0 * 32;
             if constexpr (XMODE == X_SWIGLU) {  // h = fp16(silu(acc_gate) * acc_up)  (quant/fused_mlp.py:163-165)
-                for (int c = tid; c < nsteps * 4; c += kThreads) {
+                for (int c = tc.ttid; c < nseg * 4; c += kTeamThreads) {
                     const int k = kbeg + c * 8;
-                    uint32_t o[4];
-                    const float4 g0 = *reinterpret_cast<const float4*>(p.acc_g + k), g1 = *reinterpret_cast<const float4*>(p.acc_g + k + 4);
-                    const float4 u0 = *reinterpret_cast<const float4*>(p.acc_u + k), u1 = *reinterpret_cast<const float4*>(p.acc_u + k + 4);
-                    o[0] = h2_as_u32(__floats2half2_rn(swiglu(g0.x, u0.x), swiglu(g0.y, u0.y)));
-                    o[1] = h2_as_u32(__floats2half2_rn(swiglu(g0.z, u0.z), swiglu(g0.w, u0.w)));
-                    o[2] = h2_as_u32(__floats2half2_rn(swiglu(g1.x, u1.x), swiglu(g1.y, u1.y)));
-                    o[3] = h2_as_u32(__floats2half2_rn(swiglu(g1.z, u1.z), swiglu(g1.w, u1.w)));
-                    store_perm8(xs + c * 8, o[0], o[1], o[2], o[3]);
+                    const float4 g0 = ld_cg4(p.acc_g + k), g1 = ld_cg4(p.acc_g + k + 4);
+                    const float4 u0 = ld_cg4(p.acc_u + k), u1 = ld_cg4(p.acc_u + k + 4);
+                    const uint32_t o0 = h2_as_u32(__floats2half2_rn(swiglu(g0.x, u0.x), swiglu(g0.y, u0.y)));
+                    const uint32_t o1 = h2_as_u32(__floats2half2_rn(swiglu(g0.z, u0.z), swiglu(g0.w, u0.w)));
+                    const uint32_t o2 = h2_as_u32(__floats2half2_rn(swiglu(g1.x, u1.x), swiglu(g1.y, u1.y)));
+                    const uint32_t o3 = h2_as_u32(__floats2half2_rn(swiglu(g1.z, u1.z), swiglu(g1.w, u1.w)));
+                    *reinterpret_cast<uint4*>(tc.xseg + c * 8) = perm8(o0, o1, o2, o3);
                 }
-            } else {  // attention output: one thread per feature combines the split-KV partials of its head (coalesced over d)
-                const int nvalid = min(p.nsplit, p.positions[0] / kAttnChunk + 1);
-                for (int e = tid; e < nsteps * 32; e += kThreads) {
+            } else {  // attention output: one thread per feature merges the partial records of its head
+                const int Tlen = step_pos(p) + 1;
+                const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
+                const unsigned Ua = (unsigned)(p.n_heads * upb);
+                for (int e = tc.ttid; e < nseg * 32; e += kTeamThreads) {
                     int k = kbeg + e;
                     if constexpr (ACT) {
                         if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
                     }
                     const int head = k / kHD, d = k - head * kHD;
-                    const float* src = p.part + (size_t)head * p.nsplit * kRec;
-                    float M = -INFINITY;
-                    for (int sI = 0; sI < nvalid; ++sI) M = fmaxf(M, src[(size_t)sI * kRec]);
-                    float L = 0.f, O = 0.f;
-#pragma unroll 4
-                    for (int sI = 0; sI < nvalid; ++sI) {
-                        const float* ps = src + (size_t)sI * kRec;
-                        const float wgt = expf(ps[0] - M);
-                        L = fmaf(ps[1], wgt, L);
-                        O = fmaf(ps[4 + d], wgt, O);
+                    const int hu0 = head * upb, hu1 = hu0 + upb;
+                    // teams whose unit range meets [hu0, hu1)
+                    const unsigned Tlo = ((unsigned)hu0 * tc.nb) / Ua;
+                    float M = -INFINITY, Lsum = 0.f, O = 0.f;
+                    for (unsigned Tt = Tlo; Tt < tc.nb; ++Tt) {
+                        int a, b;
+                        team_range(Tt, Ua, tc.nb, a, b);
+                        if (a >= hu1) break;
+                        if (b <= hu0 || a >= b) continue;
+                        const float* rec = p.part + ((size_t)Tt * 2 + (a >= hu0 ? 0 : 1)) * kRec;
+                        const float m = ld_cg(rec), lv = ld_cg(rec + 1), ov = ld_cg(rec + 4 + d);
+                        const float Mn = fmaxf(M, m);
+                        const float wa = (M == -INFINITY) ? 0.f : expf(M - Mn), wb = (m == -INFINITY) ? 0.f : expf(m - Mn);
+                        Lsum = Lsum * wa + lv * wb;
+                        O = O * wa + ov * wb;
+                        M = Mn;
                     }
+                    __half hv = __float2half_rn(O / Lsum);
                     const int j8 = e & 7;
-                    xs[(e & ~7) + ((j8 & 3) << 1) + (j8 >> 2)] = __float2half_rn(O / L);  // k-permuted position inside the run of 8
+                    if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
+                    tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
                 }
             }
-            cta_sync();
-            xaddr = smem_u32(xs) + (t * 8) * 2;
+            team_sync(tc.team);
+            compute_xsum(tc.xseg, nseg, tc.xsum_seg, tc.ttid, kTeamThreads);
+            team_sync(tc.team);
+            xaddr = smem_u32(tc.xseg) + (t * 8) * 2;
+            xsum = tc.xsum_seg;
         }
 
-        float acc[NW][2][4];
+        float tot[4] = {0.f, 0.f, 0.f, 0.f};
+        int ks = ks0, left = nseg;
+#pragma unroll 1
+        while (left > 0) {
+            const int n = stage_steps(ks, gs_steps, left);
+            const uint32_t st = cons_wait(ring);
+            float acc0[4], acc1[4];
+            float xs4;
+            if (n == kStageSteps) {
+                uint4 q[4], xf[4];
 #pragma unroll
-        for (int w = 0; w < NW; ++w)
+                for (int j = 0; j < 4; ++j) q[j] = lds128(st + lane_w + j * 4 * kRowPitch);
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[w][h][i] = 0.f;
-
-#pragma unroll
-        for (int w = 0; w < NW; ++w) build_group_const(gc[w], raw[w], zshift);
-        int steps_left_in_grp = gs_steps - (ks0 % gs_steps);
-        if (steps_left_in_grp < nsteps) {
-#pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                raw[w] = load_group_raw(scp[w], qzp[w]);
-                scp[w] += N;
-                qzp[w] += N >> 3;
-            }
-        }
-
-        // software pipeline: the NEXT tile's wait + shared-memory load are issued before the current tile's math, so the
-        // ~120 cycles of mbarrier-probe + LDS latency overlap with ~80 instructions of dequant/MMA
-        auto fetch = [&](uint4& q, uint32_t& bar_of_q) {
-#ifdef GPTQ_TRACE
-            const long long tw0 = clock64();
-#endif
-            mbar_wait(pipe.bar, pipe.parity);  // the tile has landed
-#ifdef GPTQ_TRACE
-            wait_cycles += clock64() - tw0;
-#endif
-            q = lds128(pipe.tile);
-            bar_of_q = pipe.bar;
-            pipe.tile += kTile;
-            pipe.bar += 8;
-            if (--pipe.left == 0) {  // ring wrap: next round, other parity
-                pipe.left = kStages;
-                pipe.tile -= kStages * kTile;
-                pipe.bar -= kStages * 8;
-                pipe.parity ^= 1u;
-            }
-        };
-        uint4 q_cur;
-        uint32_t bar_cur;
-        fetch(q_cur, bar_cur);
-#pragma unroll kStepUnroll
-        for (int step = 0; step < nsteps; ++step) {
-            if (steps_left_in_grp == 0) {
-#pragma unroll
-                for (int w = 0; w < NW; ++w) build_group_const(gc[w], raw[w], zshift);
-                steps_left_in_grp = gs_steps;
-                if (step + gs_steps < nsteps) {
-#pragma unroll
-                    for (int w = 0; w < NW; ++w) {
-                        raw[w] = load_group_raw(scp[w], qzp[w]);
-                        scp[w] += N;
-                        qzp[w] += N >> 3;
-                    }
+                for (int j = 0; j < 4; ++j) xf[j] = lds128(xaddr + j * 64);
+                step_mma<true>(q[0], xf[0], acc0, acc1);
+                step_mma<false>(q[1], xf[1], acc0, acc1);
+                step_mma<false>(q[2], xf[2], acc0, acc1);
+                step_mma<false>(q[3], xf[3], acc0, acc1);
+                xs4 = (xsum[0] + xsum[1]) + (xsum[2] + xsum[3]);
+            } else {
+                {
+                    const uint4 q = lds128(st + lane_w), xf = lds128(xaddr);
+                    step_mma<true>(q, xf, acc0, acc1);
+                    xs4 = xsum[0];
+                }
+#pragma unroll 1
+                for (int j = 1; j < n; ++j) {
+                    const uint4 q = lds128(st + lane_w + j * 4 * kRowPitch), xf = lds128(xaddr + j * 64);
+                    step_mma<false>(q, xf, acc0, acc1);
+                    xs4 += xsum[j];
                 }
             }
-            --steps_left_in_grp;
-            const uint4 xf = lds128(xaddr);
-            xaddr += 64;
+            // group epilogue: tot += s * (acc * unit - z * sum(x))   (z = stored zero + 1, quant/quant_linear.py:120-121)
+            {
+                uint2 sv;
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sv.x), "=r"(sv.y) : "r"(st + lane_s));
+                uint32_t zw;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(st + lane_z));
+                zw >>= zshift;
+                const float2 s01 = __half22float2(u32_as_h2(sv.x)), s23 = __half22float2(u32_as_h2(sv.y));
+                const float sc[4] = {s01.x, s01.y, s23.x, s23.y};
+                const float av[4] = {acc0[0], acc0[2], acc1[0], acc1[2]};  // batch row 0 of columns 4g .. 4g+3
 #pragma unroll
-            for (int w = 0; w < NW; ++w) {
-                uint4 q_next = q_cur;
-                uint32_t bar_next = bar_cur;
-                if (w + 1 < NW || step + 1 < nsteps) fetch(q_next, bar_next);  // prefetch the following tile of this segment
-                uint32_t wf[4][4];
-                dequant8<0>(q_cur.x, gc[w].za01, gc[w].zb01, gc[w].s01, wf[0]);
-                dequant8<1>(q_cur.y, gc[w].za01, gc[w].zb01, gc[w].s01, wf[1]);
-                dequant8<0>(q_cur.z, gc[w].za23, gc[w].zb23, gc[w].s23, wf[2]);
-                dequant8<1>(q_cur.w, gc[w].za23, gc[w].zb23, gc[w].s23, wf[3]);
-                mma_16816(acc[w][0], wf[0][0], wf[1][0], wf[0][1], wf[1][1], xf.x, xf.y);
-                mma_16816(acc[w][0], wf[0][2], wf[1][2], wf[0][3], wf[1][3], xf.z, xf.w);
-                mma_16816(acc[w][1], wf[2][0], wf[3][0], wf[2][1], wf[3][1], xf.x, xf.y);
-                mma_16816(acc[w][1], wf[2][2], wf[3][2], wf[2][3], wf[3][3], xf.z, xf.w);
-                __syncwarp();  // every lane has consumed the registers it read from the current tile's stage
-                if (lane == 0) mbar_arrive(bar_cur + kStages * 8);  // empty[stage]
-                q_cur = q_next;
-                bar_cur = bar_next;
+                for (int c = 0; c < 4; ++c) {
+                    const float z = (float)(((zw >> (4 * c)) & 15u) + 1u);
+                    tot[c] = fmaf(sc[c], fmaf(av[c], unit, -z * xs4), tot[c]);
+                }
             }
+            cons_release(ring, lane);
+            xaddr += n * 64;
+            xsum += n;
+            ks += n;
+            left -= n;
         }
-
-        // batch row 0 lives in the t == 0 lanes: acc[.][0][0] -> col, [0][2] -> col+1, [1][0] -> col+2, [1][2] -> col+3
-        if (t == 0) {
-            float* o0 = out0 + col;
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o0), "f"(acc[0][0][0]), "f"(acc[0][0][2]), "f"(acc[0][1][0]), "f"(acc[0][1][2]) : "memory");
-            if constexpr (DUAL) {
-                float* o1 = out1 + col;
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o1), "f"(acc[1][0][0]), "f"(acc[1][0][2]), "f"(acc[1][1][0]), "f"(acc[1][1][2])
-                             : "memory");
-            }
-        }
-        u += nsteps;
+        // all four t lanes hold the same sums: lane t == 0 publishes them
+        if (t == 0) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outp), "f"(tot[0]), "f"(tot[1]), "f"(tot[2]), "f"(tot[3]) : "memory");
+        u += nseg;
     }
-#ifdef GPTQ_TRACE
-    if (g_mega_trace != nullptr && threadIdx.x == 0) {
-        const int base = DUAL ? 40 : (XMODE == X_FULL ? 44 : (XMODE == X_ATTN ? 48 : 52));
-        g_mega_trace[blockIdx.x * 64 + base] = (unsigned long long)(clock64() - tm0);
-        g_mega_trace[blockIdx.x * 64 + base + 1] = (unsigned long long)wait_cycles;
-        g_mega_trace[blockIdx.x * 64 + base + 2] = (unsigned long long)(u_end - u_begin);
-    }
-#endif
 }
 
-// Attention work items (head, split): RoPE(q,k) from this step's cos/sin, KV append, partial softmax(qK^T)V.
-__device__ void run_attention(const MegaParams& p, int layer, float* smem_f) {
-    const int tid = threadIdx.x;
-    const int pos = p.positions[0];
-    const int T = pos + 1;
-    float* q_s = smem_f;                     // [128]
-    float* red_m = smem_f + 128;             // [32]
-    float* red_l = smem_f + 160;             // [32]
-    float* red_o = smem_f + 192;             // [32][132]
-    __half* kc_base = p.k_cache + layer * p.layer_stride;
-    __half* vc_base = p.v_cache + layer * p.layer_stride;
-    const int n_items = p.n_heads * p.nsplit;
+// ---- attention ----------------------------------------------------------------------------------------------------------
+// Work units (head, 32 keys), dealt to the teams as contiguous ranges (a team meets at most two heads); one unit = one
+// ring stage (K rows, V rows).  Per head-segment the team writes one partial record (m, l, o[128]) to p.part[T][rec].
+__device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, int layer) {
+    const int pos = step_pos(p), Tlen = pos + 1;
+    const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
+    int u, u_end;
+    team_range(tc.T, (unsigned)(p.n_heads * upb), tc.nb, u, u_end);
+    float* q_s = reinterpret_cast<float*>(tc.scratch);                   // [128]
+    __half* knew = reinterpret_cast<__half*>(tc.scratch + 512);          // [128]
+    __half* vnew = knew + kHD;                                          // [128]
+    float* red_ml = reinterpret_cast<float*>(tc.scratch + 1024);         // [8][2]
+    float* red_o = reinterpret_cast<float*>(tc.scratch + 1024 + 64);     // [8][128]
+    const int ttid = tc.ttid, lane = tc.lane, grp = ttid >> 3, j = ttid & 7;  // 32 groups of 8 lanes: group = key, lane j owns dims 8j..8j+7 and 64+8j..64+8j+7
+    const int ub_new = pos / kKeysPerUnit;  // the unit that holds this step's key
+    __half* kc_l = p.k_cache + layer * p.layer_stride;
+    __half* vc_l = p.v_cache + layer * p.layer_stride;
+    int rec = 0;
 #pragma unroll 1
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int head = item / p.nsplit, split = item - head * p.nsplit;
-        const int c0 = split * kAttnChunk;
-        if (c0 >= T) continue;
-        const int c1 = min(c0 + kAttnChunk, T);
-        __half* kc = kc_base + (size_t)head * p.max_seq * kHD;
-        __half* vc = vc_base + (size_t)head * p.max_seq * kHD;
-        cta_sync();  // smem reuse across items
-        if (tid < kHD) {
-            const int i = tid & 63;
-            const bool hi = tid >= 64;
+    while (u < u_end) {
+        const int head = u / upb, b0 = u - head * upb;
+        const int nseg = min(upb - b0, u_end - u);
+        const bool owns_new = (ub_new >= b0 && ub_new < b0 + nseg);
+        team_sync(tc.team);  // scratch reuse across segments
+        if (ttid < kHD) {
+            const int i = ttid & 63;
+            const bool hi = ttid >= 64;
             const float c = p.rope_cs[i], s = p.rope_cs[64 + i];
             const float* aq = p.acc_qkv + head * kHD;
-            const float qx = __half2float(__float2half_rn(aq[i])), qy = __half2float(__float2half_rn(aq[i + 64]));  // the qkv projection output is fp16
+            const float qx = __half2float(__float2half_rn(ld_cg(aq + i))), qy = __half2float(__float2half_rn(ld_cg(aq + i + 64)));  // the qkv projection output is fp16
             const float qr = hi ? __fadd_rn(__fmul_rn(qx, s), __fmul_rn(qy, c)) : __fsub_rn(__fmul_rn(qx, c), __fmul_rn(qy, s));
-            q_s[tid] = __half2float(__float2half_rn(qr));
-            if (pos >= c0 && pos < c1) {  // this item owns the new key/value: append them
+            q_s[ttid] = __half2float(__float2half_rn(qr));
+            if (owns_new) {  // this segment owns the new key/value: RoPE(k), append both to the cache
                 const float* ak = aq + p.H;
                 const float* av = aq + 2 * p.H;
-                const float kx = __half2float(__float2half_rn(ak[i])), ky = __half2float(__float2half_rn(ak[i + 64]));
+                const float kx = __half2float(__float2half_rn(ld_cg(ak + i))), ky = __half2float(__float2half_rn(ld_cg(ak + i + 64)));
                 const float kr = hi ? __fadd_rn(__fmul_rn(kx, s), __fmul_rn(ky, c)) : __fsub_rn(__fmul_rn(kx, c), __fmul_rn(ky, s));
-                kc[(size_t)pos * kHD + tid] = __float2half_rn(kr);
-                vc[(size_t)pos * kHD + tid] = __float2half_rn(av[tid]);
+                const __half kh = __float2half_rn(kr), vh = __float2half_rn(ld_cg(av + ttid));
+                knew[ttid] = kh;
+                vnew[ttid] = vh;
+                const size_t off = ((size_t)head * p.max_seq + pos) * kHD + ttid;
+                kc_l[off] = kh;
+                vc_l[off] = vh;
             }
         }
-        cta_sync();
-        const int grp = tid >> 3, j = tid & 7;  // 32 groups of 8 lanes; lane j owns dims [16j, 16j+16)
-        constexpr int ITER = kAttnPass / 32;
+        team_sync(tc.team);
         float qr[16];
 #pragma unroll
-        for (int d = 0; d < 16; ++d) qr[d] = q_s[16 * j + d];
-        // running online-softmax state of this lane group over the item's passes
+        for (int d = 0; d < 8; ++d) {
+            qr[d] = q_s[8 * j + d];
+            qr[8 + d] = q_s[64 + 8 * j + d];
+        }
         float mloc = -INFINITY, lloc = 0.f, o[16];
 #pragma unroll
         for (int d = 0; d < 16; ++d) o[d] = 0.f;
 #pragma unroll 1
-        for (int p0 = c0; p0 < c1; p0 += kAttnPass) {
-            // all K and V rows of this lane for the pass are requested up front (clamped indices): two DRAM round trips per pass
-            uint4 kreg[ITER][2], vreg[ITER][2];
-#pragma unroll
-            for (int it = 0; it < ITER; ++it) {
-                const int tk = min(p0 + grp + it * 32, c1 - 1);
-                const uint4* kp = reinterpret_cast<const uint4*>(kc + (size_t)tk * kHD + 16 * j);
-                kreg[it][0] = kp[0];
-                kreg[it][1] = kp[1];
+        for (int b = b0; b < b0 + nseg; ++b) {
+            const uint32_t st = cons_wait(ring);
+            if (b == ub_new) {
+                // the stage was fetched before this step's key/value existed: patch its row from the fresh values
+                team_sync(tc.team);  // (uniform per team) every warp has seen the stage land
+                const int row = pos - b * kKeysPerUnit;
+                if (ttid < 16) {
+                    sts128(st + row * 256 + ttid * 16, reinterpret_cast<const uint4*>(knew)[ttid]);
+                    fence_proxy_async_smem();  // generic-proxy writes into a stage the TMA unit will overwrite later
+                } else if (ttid < 32) {
+                    sts128(st + kVOff + row * 256 + (ttid - 16) * 16, reinterpret_cast<const uint4*>(vnew)[ttid - 16]);
+                    fence_proxy_async_smem();
+                }
+                team_sync(tc.team);
             }
-#pragma unroll
-            for (int it = 0; it < ITER; ++it) {
-                const int tk = min(p0 + grp + it * 32, c1 - 1);
-                const uint4* vp = reinterpret_cast<const uint4*>(vc + (size_t)tk * kHD + 16 * j);
-                vreg[it][0] = vp[0];
-                vreg[it][1] = vp[1];
-            }
-            float sc[ITER];
-            float mpass = -INFINITY;
-#pragma unroll
-            for (int it = 0; it < ITER; ++it) {
-                const int tk = p0 + grp + it * 32;
-                const uint32_t w[8] = {kreg[it][0].x, kreg[it][0].y, kreg[it][0].z, kreg[it][0].w, kreg[it][1].x, kreg[it][1].y, kreg[it][1].z, kreg[it][1].w};
-                float s = 0.f;
+            const int key = b * kKeysPerUnit + grp;
+            const bool valid = key < Tlen;
+            float s = 0.f;
+            if (valid) {
+                const uint4 k0 = lds128(st + grp * 256 + j * 16), k1 = lds128(st + grp * 256 + 128 + j * 16);
+                const uint32_t w[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float2 f = __half22float2(u32_as_h2(w[e]));
                     s = fmaf(qr[2 * e], f.x, s);
                     s = fmaf(qr[2 * e + 1], f.y, s);
                 }
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                s = (tk < c1) ? s * p.scale : -INFINITY;
-                sc[it] = s;
-                mpass = fmaxf(mpass, s);
             }
-            const float mnew = fmaxf(mloc, mpass);
-            if (mnew != -INFINITY) {
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (valid) {
+                s *= p.scale;
+                const float mnew = fmaxf(mloc, s);
                 const float alpha = (mloc == -INFINITY) ? 0.f : expf(mloc - mnew);
-                lloc *= alpha;
+                const float pw = expf(s - mnew);
+                lloc = fmaf(lloc, alpha, pw);
+                const uint4 v0 = lds128(st + kVOff + grp * 256 + j * 16), v1 = lds128(st + kVOff + grp * 256 + 128 + j * 16);
+                const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-                for (int d = 0; d < 16; ++d) o[d] *= alpha;
-#pragma unroll
-                for (int it = 0; it < ITER; ++it) {
-                    const int tk = p0 + grp + it * 32;
-                    const float pw = (tk < c1) ? expf(sc[it] - mnew) : 0.f;
-                    lloc += pw;
-                    const uint32_t w[8] = {vreg[it][0].x, vreg[it][0].y, vreg[it][0].z, vreg[it][0].w, vreg[it][1].x, vreg[it][1].y, vreg[it][1].z, vreg[it][1].w};
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) {
-                        const float2 f = __half22float2(u32_as_h2(w[e]));
-                        o[2 * e] = fmaf(pw, f.x, o[2 * e]);
-                        o[2 * e + 1] = fmaf(pw, f.y, o[2 * e + 1]);
-                    }
+                for (int e = 0; e < 8; ++e) {
+                    const float2 f = __half22float2(u32_as_h2(w[e]));
+                    o[2 * e] = fmaf(o[2 * e], alpha, pw * f.x);
+                    o[2 * e + 1] = fmaf(o[2 * e + 1], alpha, pw * f.y);
                 }
                 mloc = mnew;
             }
+            cons_release(ring, lane);
         }
-        if (j == 0) {
-            red_m[grp] = mloc;
-            red_l[grp] = lloc;
-        }
+        // merge the 4 key groups of the warp (lanes xor 8, 16), then the 8 warps through shared memory
 #pragma unroll
-        for (int d = 0; d < 16; ++d) red_o[grp * 132 + 16 * j + d] = o[d];
-        cta_sync();
-        if (tid < kHD) {
-            float M = -INFINITY;
-#pragma unroll 8
-            for (int gI = 0; gI < 32; ++gI) M = fmaxf(M, red_m[gI]);
-            float L = 0.f, O = 0.f;
-#pragma unroll 8
-            for (int gI = 0; gI < 32; ++gI) {
-                const float wgt = (red_m[gI] == -INFINITY) ? 0.f : expf(red_m[gI] - M);
-                L = fmaf(red_l[gI], wgt, L);
-                O = fmaf(red_o[gI * 132 + tid], wgt, O);
+        for (int sh = 8; sh <= 16; sh <<= 1) {
+            const float mo = __shfl_xor_sync(0xffffffffu, mloc, sh), lo = __shfl_xor_sync(0xffffffffu, lloc, sh);
+            const float mn = fmaxf(mloc, mo);
+            const float wa = (mloc == -INFINITY) ? 0.f : expf(mloc - mn), wb = (mo == -INFINITY) ? 0.f : expf(mo - mn);
+            lloc = lloc * wa + lo * wb;
+#pragma unroll
+            for (int d = 0; d < 16; ++d) {
+                const float oo = __shfl_xor_sync(0xffffffffu, o[d], sh);
+                o[d] = o[d] * wa + oo * wb;
             }
-            float* dst = p.part + ((size_t)head * p.nsplit + split) * kRec;
-            dst[4 + tid] = O;
-            if (tid == 0) {
+            mloc = mn;
+        }
+        if (lane < 8) {
+            if (lane == 0) {
+                red_ml[tc.wt * 2] = mloc;
+                red_ml[tc.wt * 2 + 1] = lloc;
+            }
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                red_o[tc.wt * kHD + 8 * lane + d] = o[d];
+                red_o[tc.wt * kHD + 64 + 8 * lane + d] = o[8 + d];
+            }
+        }
+        team_sync(tc.team);
+        if (ttid < kHD) {
+            float M = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < kTeamWarps; ++w) M = fmaxf(M, red_ml[w * 2]);
+            float L = 0.f, O = 0.f;
+#pragma unroll
+            for (int w = 0; w < kTeamWarps; ++w) {
+                const float mw = red_ml[w * 2];
+                const float wgt = (mw == -INFINITY) ? 0.f : expf(mw - M);
+                L = fmaf(red_ml[w * 2 + 1], wgt, L);
+                O = fmaf(red_o[w * kHD + ttid], wgt, O);
+            }
+            float* dst = p.part + ((size_t)tc.T * 2 + rec) * kRec;
+            dst[4 + ttid] = O;
+            if (ttid == 0) {
                 dst[0] = M;
                 dst[1] = L;
             }
         }
+        ++rec;
+        u += nseg;
+    }
+}
+
+// ---- lm_head: fp16 [V, H] rows through the ring, lm_rows whole rows per stage -------------------------------------------------
+__device__ void run_lm_head(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, const __half* xs_plain) {
+    const int R = p.lm_rows, H = p.H, nch = H / 8;
+    int u, u_end;
+    team_range(tc.T, (unsigned)((p.V + R - 1) / R), tc.nb, u, u_end);
+    float* part_s = reinterpret_cast<float*>(tc.scratch);  // [2][R][8]
+    // this thread's chunks of x (k = 8 * (ttid + 256 i)) stay in registers for the whole op
+    float xr[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int c = tc.ttid + i * kTeamThreads;
+        if (c < nch) {
+            const uint4 v = *reinterpret_cast<const uint4*>(xs_plain + c * 8);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(u32_as_h2(w[e]));
+                xr[i][2 * e] = f.x;
+                xr[i][2 * e + 1] = f.y;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) xr[i][e] = 0.f;
+        }
+    }
+    int buf = 0;
+#pragma unroll 1
+    for (; u < u_end; ++u) {
+        const int nrows = min(R, p.V - u * R);
+        const uint32_t st = cons_wait(ring);
+        float* ps = part_s + buf * (R * kTeamWarps);
+#pragma unroll 1
+        for (int r = 0; r < nrows; ++r) {
+            float a = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = tc.ttid + i * kTeamThreads;
+                if (c < nch) {
+                    const uint4 wv = lds128(st + (uint32_t)(r * H * 2 + c * 16));
+                    const uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __half22float2(u32_as_h2(w[e]));
+                        a = fmaf(f.x, xr[i][2 * e], a);
+                        a = fmaf(f.y, xr[i][2 * e + 1], a);
+                    }
+                }
+            }
+            a = warp_sum(a);
+            if (tc.lane == 0) ps[r * kTeamWarps + tc.wt] = a;
+        }
+        cons_release(ring, tc.lane);
+        team_sync(tc.team);  // partials of this stage are visible; the other buffer is free again
+        if (tc.ttid < nrows) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < kTeamWarps; ++w) a += ps[tc.ttid * kTeamWarps + w];
+            p.logits[(size_t)u * R + tc.ttid] = __float2half_rn(a);
+        }
+        buf ^= 1;
     }
 }
 
 template <bool ACT>
-__global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __grid_constant__ MegaParams p) {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ float red_s[kWarps];
-    __shared__ __align__(8) unsigned long long bars_s[2 * kStages];
+__global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __grid_constant__ MegaParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    __shared__ float red_s[kConsumerWarps];
+    __shared__ __align__(8) unsigned long long bars_s[kTeams][2 * kMaxStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // smem: [ring: 15 x 4224 B][xs: H halves][tmp: H halves / attention scratch]
-    constexpr int kRingBytes = ((kStages * kTile + 127) / 128) * 128;
-    __half* xs = reinterpret_cast<__half*>(smem_raw + kRingBytes);
-    __half* tmp = xs + p.H;
-    Pipe pipe;
-    pipe.ring = smem_u32(smem_raw);
-    pipe.full = smem_u32(&bars_s[0]);
-    pipe.empty = smem_u32(&bars_s[kStages]);
-    pipe.tile = pipe.ring + (lane & 3) * kRowPitch + (warp & 7) * 128 + (lane >> 2) * 16;  // row t of the tile, this lane's 4 columns
-    pipe.bar = pipe.full;
-    pipe.parity = 0;
-    pipe.left = kStages;
+    // smem: [team 0 ring][team 1 ring][xs: H halves][xsum: H/32 floats][tmp / team scratch]
+    const uint32_t ring_bytes = (uint32_t)p.n_stages * kStageBytes;
+    __half* xs = reinterpret_cast<__half*>(smem_raw + kTeams * ring_bytes);
+    float* xsum = reinterpret_cast<float*>(xs + p.H);
+    uint8_t* tmp_raw = reinterpret_cast<uint8_t*>(xsum + p.H / 32);
+    tmp_raw += (16 - (reinterpret_cast<uintptr_t>(tmp_raw) & 15)) & 15;
+    __half* tmp = reinterpret_cast<__half*>(tmp_raw);
+
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) {
-            mbar_init(pipe.full + s * 8, 1);
-            mbar_init(pipe.empty + s * 8, kWarps);
-        }
+        for (int tm = 0; tm < kTeams; ++tm)
+            for (int s = 0; s < p.n_stages; ++s) {
+                mbar_init(smem_u32(&bars_s[tm][s]), 1);
+                mbar_init(smem_u32(&bars_s[tm][kMaxStages + s]), kTeamWarps);
+            }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    __syncthreads();  // the only block-wide barrier: after it the producer warp and the consumers never meet again
-    if (warp >= kWarps) {
-        if (lane == 0) producer_loop(p, pipe.ring, pipe.full, pipe.empty, warp - kWarps);
+    __syncthreads();  // the only block-wide barrier: after it the producer warps and the consumers never meet again
+    const unsigned nb = gridDim.x * kTeams;
+    if (warp >= kConsumerWarps) {
+        if (lane == 0) {
+            const int tm = warp - kConsumerWarps;
+            ProdRing r;
+            r.ring = smem_u32(smem_raw) + tm * ring_bytes;
+            r.full = smem_u32(&bars_s[tm][0]);
+            r.empty = smem_u32(&bars_s[tm][kMaxStages]);
+            r.stage = 0;
+            r.use = 0;
+            r.nstages = p.n_stages;
+            producer_loop(p, r, blockIdx.x * kTeams + tm, nb);
+        }
         return;
     }
+    TeamCtx tc;
+    tc.team = warp / kTeamWarps;
+    tc.wt = warp % kTeamWarps;
+    tc.lane = lane;
+    tc.ttid = tid - tc.team * kTeamThreads;
+    tc.T = blockIdx.x * kTeams + tc.team;
+    tc.nb = nb;
+    tc.xseg = xs + tc.team * (p.H / 2);
+    tc.xsum_seg = xsum + tc.team * (p.H / 64);
+    tc.scratch = tmp_raw + tc.team * kTeamScratch;
+    ConsRing ring;
+    ring.ring = smem_u32(smem_raw) + tc.team * ring_bytes;
+    ring.full = smem_u32(&bars_s[tc.team][0]);
+    ring.tile = ring.ring;
+    ring.bar = ring.full;
+    ring.parity = 0;
+    ring.left = p.n_stages;
+    ring.nstages = p.n_stages;
+
     unsigned long long gen;  // barrier target (meaningful in thread 0): the counter value when this launch began
     {
+        // bar[1] = counter value at the end of the previous launch (written by CTA 0 after its last barrier): CTAs that
+        // start late may already see arrivals of this launch in bar[0], never in bar[1]
         unsigned long long v;
-        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar) : "memory");
-        gen = v - (v % gridDim.x);  // CTAs that already arrived at the first barrier have added < gridDim.x
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar + 1) : "memory");
+        gen = v;
     }
 
     // this step's RoPE angles (quant/fused_attn.py:43,91): freq_i = exp(i * inv_base) * pos
     if (blockIdx.x == 0 && tid < 64) {
-        const float f = expf((float)tid * p.inv_base) * (float)p.positions[0];
+        const float f = expf((float)tid * p.inv_base) * (float)step_pos(p);
         p.rope_cs[tid] = cosf(f);
         p.rope_cs[64 + tid] = sinf(f);
     }
 
     // residual stream: every stage_norm reads buffer `cur` (or the embedding row) and writes the other one
-    const __half* resid_src = p.embed + (size_t)p.tokens[0] * p.H;
+    const int token = min(max(p.tokens[0], 0), p.V - 1);
+    const __half* resid_src = p.embed + (size_t)token * p.H;
     const float* resid_acc = nullptr;
     int cur = 1;
 #pragma unroll 1
@@ -689,151 +935,168 @@ __global__ void __launch_bounds__(kBlock, 2) llama_decode_mega_kernel(const __gr
         const LayerDesc& L = p.layers[l];
         // ---- Q ----
         MTRACE(l * 12 + 0);
-        stage_norm<ACT>(p, resid_src, resid_acc, L.input_norm, p.resid[cur ^ 1], xs, tmp, red_s, L.qkv_perm);
+        stage_norm<ACT, false>(p, resid_src, resid_acc, L.input_norm, p.resid[cur ^ 1], xs, xsum, tmp, red_s, L.qkv_perm);
         MTRACE(l * 12 + 1);
         cur ^= 1;
         zero_slice(p.acc_g, p.I);  // last read by the previous layer's D
         zero_slice(p.acc_u, p.I);
-        cta_sync();
-        run_matvec<false, X_FULL>(p, pipe, L.qkv, L.qkv, p.H, 3 * p.H, p.acc_qkv, nullptr, xs);
+        run_matvec<1, X_FULL>(p, ring, tc, L.qkv.gs_steps, p.H, 3 * p.H, p.acc_qkv, nullptr, xs, xsum);
         MTRACE(l * 12 + 2);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 3);
         // ---- A ----
         zero_slice(p.acc_d, p.H);  // last read by this layer's Q
-        run_attention(p, l, reinterpret_cast<float*>(tmp));
+        run_attention(p, ring, tc, l);
         MTRACE(l * 12 + 4);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 5);
         // ---- O ----
         zero_slice(p.acc_qkv, 3 * p.H);
-        run_matvec<false, X_ATTN, ACT>(p, pipe, L.o, L.o, p.H, p.H, p.acc_o, nullptr, xs, L.o_perm);
+        run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.H, p.H, p.acc_o, nullptr, xs, xsum, L.o_perm);
         MTRACE(l * 12 + 6);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 7);
         // ---- G ----
-        stage_norm<ACT>(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, tmp, red_s, L.mlp_perm);
+        stage_norm<ACT, false>(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, xsum, tmp, red_s, L.mlp_perm);
         cur ^= 1;
-        cta_sync();
         MTRACE(l * 12 + 8);
-        run_matvec<true, X_FULL>(p, pipe, L.gate, L.up, p.H, p.I, p.acc_g, p.acc_u, xs);
+        run_matvec<2, X_FULL>(p, ring, tc, L.gate.gs_steps, p.H, p.I, p.acc_g, p.acc_u, xs, xsum);
         MTRACE(l * 12 + 9);
         grid_barrier(p.bar, gen);
         // ---- D ----
         zero_slice(p.acc_o, p.H);
         MTRACE(l * 12 + 10);
-        run_matvec<false, X_SWIGLU>(p, pipe, L.down, L.down, p.I, p.H, p.acc_d, nullptr, xs);
+        run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.acc_d, nullptr, xs, xsum);
         MTRACE(l * 12 + 11);
         grid_barrier(p.bar, gen);
         resid_src = p.resid[cur];
         resid_acc = p.acc_d;
     }
-    // ---- L: final norm + lm_head (fp16 [V, H] rows, one warp per row) ----
-    stage_norm<false>(p, resid_src, resid_acc, p.final_norm, nullptr, xs, tmp, red_s, nullptr);
+    // ---- L: final norm + lm_head ----
+    stage_norm<false, true>(p, resid_src, resid_acc, p.final_norm, nullptr, xs, xsum, tmp, red_s, nullptr);
     zero_slice(p.acc_g, p.I);
     zero_slice(p.acc_u, p.I);
-    cta_sync();
-    {
-        const int chunks = p.H / 8;
-#pragma unroll 1
-        for (int row = blockIdx.x * kWarps + warp; row < p.V; row += gridDim.x * kWarps) {
-            const uint4* wr = reinterpret_cast<const uint4*>(p.lm_head + (size_t)row * p.H);
-            float a = 0.f;
-#pragma unroll 4
-            for (int c = lane; c < chunks; c += 32) {
-                uint4 wv;
-                asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(wv.x), "=r"(wv.y), "=r"(wv.z), "=r"(wv.w) : "l"(wr + c));
-                // xs is k-permuted: chunk c holds (k0,k4)(k1,k5)(k2,k6)(k3,k7)
-                const uint4 xv = *reinterpret_cast<const uint4*>(xs + c * 8);
-                const uint32_t wp[4] = {__byte_perm(wv.x, wv.z, 0x5410), __byte_perm(wv.x, wv.z, 0x7632), __byte_perm(wv.y, wv.w, 0x5410),
-                                        __byte_perm(wv.y, wv.w, 0x7632)};
-                const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 wf = __half22float2(u32_as_h2(wp[e])), xf = __half22float2(u32_as_h2(xw[e]));
-                    a = fmaf(wf.x, xf.x, a);
-                    a = fmaf(wf.y, xf.y, a);
-                }
-            }
-            a = warp_sum(a);
-            if (lane == 0) p.logits[row] = __float2half_rn(a);
-        }
-    }
+    run_lm_head(p, ring, tc, xs);
     grid_barrier(p.bar, gen);
     zero_slice(p.acc_d, p.H);
-    if (blockIdx.x == 0 && p.next_token != nullptr) {  // greedy argmax (lowest index wins ties)
-        float best = -INFINITY;
-        int idx = 0x7fffffff;
-        for (int i = tid; i < p.V; i += kThreads) {
-            const float v = __half2float(p.logits[i]);
-            if (v > best || (v == best && i < idx)) {
-                best = v;
-                idx = i;
-            }
-        }
-        __shared__ float sv[kWarps];
-        __shared__ int si[kWarps];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
-            if (ov > best || (ov == best && oi < idx)) {
-                best = ov;
-                idx = oi;
-            }
-        }
-        if (lane == 0) {
-            sv[warp] = best;
-            si[warp] = idx;
-        }
-        cta_sync();
-        if (tid == 0) {
-            for (int w = 1; w < kWarps; ++w)
-                if (sv[w] > best || (sv[w] == best && si[w] < idx)) {
-                    best = sv[w];
-                    idx = si[w];
+    if (blockIdx.x == 0) {
+        if (tid == 0) p.bar[1] = gen;  // every CTA has arrived at the last barrier: the counter rests at this value until the next launch
+        if (p.next_token != nullptr) {  // greedy argmax (lowest index wins ties)
+            float best = -INFINITY;
+            int idx = 0x7fffffff;
+            for (int i = tid; i < p.V; i += kConsumers) {
+                const float v = __half2float(p.logits[i]);
+                if (v > best || (v == best && i < idx)) {
+                    best = v;
+                    idx = i;
                 }
-            p.next_token[0] = idx;
+            }
+            __shared__ float sv[kConsumerWarps];
+            __shared__ int si[kConsumerWarps];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+                if (ov > best || (ov == best && oi < idx)) {
+                    best = ov;
+                    idx = oi;
+                }
+            }
+            if (lane == 0) {
+                sv[warp] = best;
+                si[warp] = idx;
+            }
+            cta_sync();
+            if (tid == 0) {
+                for (int w = 1; w < kConsumerWarps; ++w)
+                    if (sv[w] > best || (sv[w] == best && si[w] < idx)) {
+                        best = sv[w];
+                        idx = si[w];
+                    }
+                p.next_token[0] = idx;
+            }
         }
     }
 }
 
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// device properties that shape the launch (queried per call: no cached global state)
+struct MegaPlan {
+    int grid, n_stages, lm_rows;
+    size_t smem;
+};
+
+// Shared-memory plan for this model on a device with `sms` SMs and `smem_max` bytes of opt-in shared memory per block;
+// returns false if the shape does not fit the kernel's staging buffers.
+bool mega_plan(const gptq_llama_model& m, int sms, size_t smem_max, MegaPlan& pl) {
+    const int H = m.hidden, I = m.intermediate;
+    const size_t fixed = (size_t)H * 2 + (size_t)(H / 32) * 4 + 16 + max((size_t)H * 2, (size_t)kTeams * kTeamScratch);
+    if (smem_max < fixed + 1024) return false;
+    int st = (int)((smem_max - fixed - 1024) / ((size_t)kTeams * kStageBytes));  // 1 KB: static shared memory of the kernel
+    st = min(st, kMaxStages);
+    if (st < 2) return false;
+    pl.grid = sms;
+    pl.n_stages = st;
+    pl.smem = fixed + (size_t)kTeams * st * kStageBytes;
+    pl.lm_rows = max(1, kLmStageBytes / (H * 2));
+    if ((size_t)pl.lm_rows * H * 2 > (size_t)kStageBytes) return false;
+    if ((size_t)2 * pl.lm_rows * kTeamWarps * 4 > (size_t)kTeamScratch) return false;
+    // per-team k-segments of o_proj / down_proj are staged in half of the xs buffer, their step sums in half of xsum
+    const long long nteams = (long long)sms * kTeams;
+    const long long seg_o = ((long long)(H / kSlabCols) * (H / 32) + nteams - 1) / nteams + 1;
+    const long long seg_d = ((long long)(H / kSlabCols) * (I / 32) + nteams - 1) / nteams + 1;
+    const long long seg = max(seg_o, seg_d);
+    if (seg * 32 > H / 2 || seg > H / 64) return false;
+    if (m.n_heads > nteams) return false;  // a team's attention range must meet at most two heads
+    // 32-bit range arithmetic of team_range: (T + 1) * U must stay below 2^32 for every operation's unit count U
+    const long long umax = max(max((long long)2 * (I / kSlabCols) * (H / 32), (long long)(H / kSlabCols) * (I / 32)),
+                               max((long long)m.vocab, (long long)m.n_heads * 4096));
+    if (umax * (nteams + 1) >= (1ll << 32)) return false;
+    return true;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
 bool mega_supported(const gptq_llama_model& m, const gptq_llama_state& st) {
-    if (getenv("GPTQ_NO_MEGA") != nullptr) return false;
     if (st.batch != 1 || m.n_layers > kMaxLayers || m.head_dim != kHD) return false;
-    if (m.hidden % kSlabCols || m.intermediate % kSlabCols || m.hidden > 8192 || m.intermediate > 28672) return false;
-    const int gs = m.layers[0].qkv.groupsize;
-    if (gs <= 0 || gs % 32) return false;
+    if (m.hidden % kSlabCols || m.intermediate % kSlabCols || m.hidden > 8192 || m.intermediate > 32768 || m.hidden % 64) return false;
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         const gptq_qweight* ws[5] = {&ly.qkv, &ly.o, &ly.gate, &ly.up, &ly.down};
-        if ((ly.qkv_perm != nullptr || ly.o_perm != nullptr || ly.mlp_perm != nullptr) && (m.hidden % 8 != 0)) return false;
         for (const gptq_qweight* w : ws) {
-            if (w->bits != 4 || w->groupsize != gs) return false;
-            if ((reinterpret_cast<uintptr_t>(w->qweight) & 15) || (reinterpret_cast<uintptr_t>(w->scales) & 7)) return false;
+            if (w->bits != 4 || w->groupsize <= 0 || w->groupsize % 32) return false;
+            if ((reinterpret_cast<uintptr_t>(w->qweight) & 15) || (reinterpret_cast<uintptr_t>(w->scales) & 15) || (reinterpret_cast<uintptr_t>(w->qzeros) & 15))
+                return false;
         }
+        if (ly.gate.groupsize != ly.up.groupsize) return false;
     }
+    if ((reinterpret_cast<uintptr_t>(m.lm_head) & 15) || (reinterpret_cast<uintptr_t>(st.k_cache) & 15) || (reinterpret_cast<uintptr_t>(st.v_cache) & 15)) return false;
     return true;
 }
 
 size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq) {
-    const int nsplit = ceil_div(max_seq, kAttnChunk);
+    (void)max_seq;
+    const size_t max_teams = 1024;  // >= kTeams * SM count of any device this library runs on
     return al256((size_t)m.hidden * 2) * 2 + al256((size_t)3 * m.hidden * 4) + al256((size_t)m.hidden * 4) * 2 + al256((size_t)m.intermediate * 4) * 2 +
-           al256((size_t)m.n_heads * nsplit * kRec * 4) + al256(128 * 4) + 256;
+           al256(max_teams * 2 * kRec * 4) + al256(128 * 4) + 256;
 }
 
 cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream) {
     static_assert(sizeof(MegaParams) < 32000, "kernel parameter space");
+    int dev = 0, sms = 0, smem_optin = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return cudaErrorInvalidDevice;
+    MegaPlan pl;
+    if (sms * kTeams > 1024 || !mega_plan(m, sms, (size_t)smem_optin, pl)) return cudaErrorInvalidConfiguration;
+
     MegaParams p{};
     p.n_layers = m.n_layers; p.H = m.hidden; p.I = m.intermediate; p.V = m.vocab; p.n_heads = m.n_heads;
-    p.groupsize = m.layers[0].qkv.groupsize;
     p.max_seq = st.max_seq;
-    p.nsplit = ceil_div(st.max_seq, kAttnChunk);
+    p.n_stages = pl.n_stages;
+    p.lm_rows = pl.lm_rows;
     p.eps = m.rms_eps;
     p.inv_base = (float)(-2.0 * log((double)m.rope_base) / (double)m.head_dim);
     p.scale = 1.0f / sqrtf((float)m.head_dim);
@@ -860,7 +1123,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     p.acc_d = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
     p.acc_g = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
     p.acc_u = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
-    p.part = reinterpret_cast<float*>(take((size_t)m.n_heads * p.nsplit * kRec * 4));
+    p.part = reinterpret_cast<float*>(take((size_t)1024 * 2 * kRec * 4));
     p.rope_cs = reinterpret_cast<float*>(take(128 * 4));
     p.bar = reinterpret_cast<unsigned long long*>(take(256));
     bool act = false;  // any act-order gather: the ACT instantiation (the plain one carries no trace of the feature)
@@ -871,6 +1134,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
             d.qw = reinterpret_cast<const uint32_t*>(w.qweight);
             d.sc = reinterpret_cast<const __half*>(w.scales);
             d.qz = reinterpret_cast<const uint32_t*>(w.qzeros);
+            d.gs_steps = w.groupsize / 32;
             return d;
         };
         p.layers[l].qkv = md(ly.qkv);
@@ -885,26 +1149,17 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
         p.layers[l].mlp_perm = ly.mlp_perm;
         act = act || ly.qkv_perm != nullptr || ly.o_perm != nullptr || ly.mlp_perm != nullptr;
     }
-    // smem: rings + xs (max(H, widest staged segment)) + tmp (H halves or the attention scratch)
-    const size_t xs_halves = (size_t)m.hidden;  // segments of the down projection are far shorter than H (checked below)
-    const size_t tmp_bytes = max((size_t)m.hidden * 2, (size_t)(192 + 32 * 132) * 4);
-    const size_t smem = (size_t)(((kStages * kTile + 127) / 128) * 128) + xs_halves * 2 + tmp_bytes;
-    // cooperative launch: every CTA must be co-resident (2 per SM on B200); if the device cannot host them, the caller
-    // falls back to the kernel-chain engine instead of risking a barrier deadlock
-    int dev = 0, sms = 0, occ = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return cudaErrorInvalidDevice;
     auto kernel = act ? llama_decode_mega_kernel<true> : llama_decode_mega_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) return cudaErrorCooperativeLaunchTooLarge;
-    const int grid = (occ >= 2 ? 2 : 1) * sms;
-    // the per-CTA k-segment of the down projection must fit in xs
-    const long long seg_steps = ((long long)(m.hidden / kSlabCols) * (m.intermediate / 32) + grid - 1) / grid;
-    if (seg_steps * 32 > (long long)xs_halves || smem > 110 * 1024) return cudaErrorInvalidConfiguration;
+    int occ = 0;
+    // cooperative launch: every CTA must be co-resident (one per SM); if the device cannot host them, the caller falls back to
+    // the kernel-chain engine instead of risking a barrier deadlock
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, pl.smem) != cudaSuccess || occ < 1) return cudaErrorCooperativeLaunchTooLarge;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
+    cfg.gridDim = dim3(pl.grid);
     cfg.blockDim = dim3(kBlock);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = pl.smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the grid barrier cannot deadlock

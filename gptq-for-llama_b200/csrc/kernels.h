@@ -44,12 +44,10 @@ cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl);
 bool gemm_tc_supported(const QLinearArgs& a);
 cudaError_t launch_qlinear_gemm_tc(const QLinearArgs& a);
 
-// decode_mega.cu -- persistent single-kernel decode step (batch 1, int4, no act-order)
+// decode_mega.cu -- persistent single-kernel decode step (batch 1, int4 kernel-form layers)
 bool mega_supported(const gptq_llama_model& m, const gptq_llama_state& st);
 size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq);
 cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream);
-// decode_mega3.cu -- same step, one CTA per SM with three consumer groups (same scratch layout)
-cudaError_t launch_decode_mega3(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream);
 
 // elementwise.cu
 cudaError_t launch_rope(void* qk, int64_t token_stride, const int64_t* position_ids, int64_t pos_batch_stride, int bsz, int seq, int rows, int head_dim,

@@ -504,7 +504,7 @@ cudaError_t launch_qlinear_skinny(const QLinearArgs& a, bool pdl) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (pdl && getenv("GPTQ_NO_PDL") == nullptr) ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     cudaError_t e;
     if (a.dual) {
         e = cudaFuncSetAttribute(qmatvec_int4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);

@@ -184,6 +184,10 @@ class LlamaDecoder:
         """Kernels of ours launched per decoded token (1 on the persistent single-kernel path)."""
         return int(lib.gptq_llama_decode_launches(ctypes.byref(self.model), ctypes.byref(self.state)))
 
+    def mega_scratch_offset(self) -> int:
+        """Byte offset of the persistent kernel's region in self.scratch (diagnostics; see gptq_llama_persistent_scratch_offset)."""
+        return int(lib.gptq_llama_persistent_scratch_offset(ctypes.byref(self.model), self.batch, self.max_seq))
+
     def step(self, stream=None):
         """Run one decode step on the tokens/positions currently in device memory."""
         if self.graph is not None:

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GPTQ_B200_ABI_VERSION 2 /* 2: gptq_llama_layer gained the act-order input gathers */
+#define GPTQ_B200_ABI_VERSION 3 /* 2: gptq_llama_layer gained the act-order input gathers; 3: gptq_llama_persistent_scratch_offset */
 
 typedef void* gptq_stream_t; /* cudaStream_t */
 
@@ -166,6 +166,10 @@ int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_llama_state
 /* Number of kernels one gptq_llama_decode_step launches for this model/state: 1 when the persistent single-kernel
  * path applies (batch 1, every layer int4 without act-order), else the per-operation kernel chain. */
 int gptq_llama_decode_launches(const gptq_llama_model* model, const gptq_llama_state* state);
+/* Diagnostics / tests: byte offset, inside the scratch area, of the persistent kernel's region.  It begins with the residual
+ * stream ping-pong: two fp16 [hidden] vectors, each padded to 256 bytes (after a step: [0] = the residual entering the last
+ * layer, [1] = the residual after the last layer's attention block). */
+size_t gptq_llama_persistent_scratch_offset(const gptq_llama_model* model, int batch, int max_seq);
 
 #ifdef __cplusplus
 }

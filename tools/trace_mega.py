@@ -1,27 +1,27 @@
+"""Device timeline of the persistent decode kernel (build with `make -C gptq-for-llama_b200/csrc variants`; run with
+GPTQ_B200_LIB=gptq-for-llama_b200/dev/libgptq_b200_trace.so).  %globaltimer per CTA at the phase boundaries of the first layers."""
 import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'gptq-for-llama_b200'))
 from gptq_b200 import engine, _lib
 raw = ctypes.CDLL(_lib.LIB_PATH)
-dec = engine.synthetic_llama('7b', max_seq=2048, use_graph=False)
+size = sys.argv[1] if len(sys.argv) > 1 else '7b'
+dec = engine.synthetic_llama(size, max_seq=2048, use_graph=False)
 dec.k_cache.normal_(0, 0.5); dec.v_cache.normal_(0, 0.5)
 dec.positions.fill_(2047); dec.tokens.fill_(1)
-buf = torch.zeros(296 * 64, dtype=torch.int64, device='cuda')
+NCTA = torch.cuda.get_device_properties(0).multi_processor_count
+buf = torch.zeros(NCTA * 64, dtype=torch.int64, device='cuda')
 raw.gptq_debug_set_mega_trace.argtypes = [ctypes.c_void_p]
 assert raw.gptq_debug_set_mega_trace(buf.data_ptr()) == 0
 for _ in range(3):
     dec.step()
 torch.cuda.synchronize()
-t = buf.cpu().view(296, 64).double()
+t = buf.cpu().view(NCTA, 64).double()
 t0 = t[:, 0].min()
 names = ['Q start', 'Q x staged', 'Q matvec done', 'Q barrier passed', 'A done', 'A barrier passed', 'O done', 'O barrier passed', 'G x staged', 'G done', 'D start(after barrier)', 'D done']
-for l in range(3):
+for l in range(1, 4):
     print(f'layer {l}: (min / median / max over CTAs, us since kernel start)')
     for k in range(12):
         c = (t[:, l * 12 + k] - t0) / 1e3
         print(f'  {names[k]:24s} {c.min().item():8.2f} {c.median().item():8.2f} {c.max().item():8.2f}')
-
-for name, base in (('G (dual)', 40), ('Q', 44), ('O', 48), ('D', 52)):
-    tot, wait, units = t[:, base], t[:, base + 1], t[:, base + 2]
-    print(f'{name}: matvec cycles median {tot.median().item():.0f}, of which waiting for tiles {wait.median().item():.0f} ({(wait / tot).median().item():.0%}); units/CTA {units.median().item():.0f}; '
-          f'cycles per tile (non-wait) {((tot - wait) / (units * (2 if base == 40 else 1))).median().item():.0f}')
+    print(f'  layer total {((t[:, (l + 1) * 12] - t[:, l * 12]) / 1e3).median().item():.2f} us')
