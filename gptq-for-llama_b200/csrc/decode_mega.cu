@@ -14,7 +14,10 @@
 //   then        L  lm_head         x = rmsnorm(resid + fp16(acc_down)), fp16 rows   -> logits;   argmax
 //
 // Matvec stage = up to 4 k-steps (16 packed rows = 128 k) x 256 columns of ONE quantisation group, plus that
-// group's 256 scales and 256 zeros.  Arithmetic (quant/quant_linear.py:113-133 regrouped): inside a group
+// group's 256 scales and 256 zeros.  The weights of a stage arrive as ONE cp.async.bulk.tensor request (3-D view of the
+// packed matrix: 128-byte column chunk x packed row x chunk index, box 32 x 16 x 8, SWIZZLE_128B so that the four rows a
+// quarter-warp reads land on distinct banks); one tensor map per row stride serves every layer (the matrices of a
+// class are addressed through the chunk coordinate).  Arithmetic (quant/quant_linear.py:113-133 regrouped): inside a group
 //      sum_k x_k (w_k - z) s  =  s * ( sum_k x_k w_k  -  z * sum_k x_k )
 // so the consumers feed the RAW nibbles to the tensor pipe (mma.sync m16n8k16, operands swapped: A = 16 output
 // columns x 16 k of weights, B = x): a nibble masked in place IS an fp16 subnormal (n * 2^-24, or 16 n * 2^-24 for
@@ -28,6 +31,9 @@
 // Split-K partial sums are accumulated with red.global.add.f32 into fp32 vectors that the NEXT operation
 // rounds to fp16 exactly where the reference rounds (a QuantLinear output is fp16); each vector is re-zeroed
 // one operation after its last reader.  Only the fp32 summation order of those partials is unordered.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 #include "common.cuh"
 #include "int4_core.cuh"
 #include "kernels.h"
@@ -44,18 +50,18 @@ constexpr int kConsumers = kTeams * kTeamThreads;     // 512
 constexpr int kConsumerWarps = kTeams * kTeamWarps;   // 16
 constexpr int kBlock = kConsumers + 32 * kTeams;      // + one producer warp per team
 constexpr int kSlabCols = 256;
-constexpr int kRowPitch = 1024 + 32;   // smem pitch of a 1 KB weight row: +32 B puts the 4 rows of a k-step on distinct bank groups
 constexpr int kStageSteps = 4;         // k-steps (of 32 k = 4 packed rows) per stage
-constexpr int kScaleOff = kStageSteps * 4 * kRowPitch;  // 16896: 256 fp16 scales of the stage's group
-constexpr int kZeroOff = kScaleOff + 512;               // 17408: 32 qzeros words (256 nibbles)
-constexpr int kStageBytes = kZeroOff + 128;             // 17536
+constexpr int kStepBytes = 4096;       // 4 packed rows x 256 columns
+constexpr int kScaleOff = kStageSteps * kStepBytes;     // 16384: 256 fp16 scales of the stage's group
+constexpr int kZeroOff = kScaleOff + 512;               // 16896: 32 qzeros words (256 nibbles)
+constexpr int kStageBytes = 17 * 1024;                  // 17408: stages are 1 KB aligned (128-byte swizzle atoms of the TMA boxes)
 constexpr int kHD = 128;
 constexpr int kKeysPerUnit = 32;       // attention work unit: 32 keys of one head = 8 KB of K + 8 KB of V = one stage
 constexpr int kVOff = 8192 + 256;      // V rows of a KV stage (K rows at offset 0)
 constexpr int kRec = kHD + 4;          // floats per attention partial record: m, l, 2 pad, o[128]
 constexpr int kMaxLayers = 80;
 constexpr int kMaxStages = 8;
-constexpr int kTeamScratch = 5632;     // per-team scratch (attention merge buffers / lm_head partials)
+constexpr int kTeamScratch = 4224;     // per-team scratch (attention merge buffers / lm_head partials)
 constexpr int kLmStageBytes = 16384;   // lm_head bytes per stage (whole rows)
 
 #ifdef GPTQ_DQ_EXACT_INT
@@ -71,7 +77,7 @@ namespace {
 
 #define MTRACE(id)                                                                                                       \
     do {                                                                                                                 \
-        if (g_mega_trace != nullptr && threadIdx.x == 0 && (id) < 64) {                                                   \
+        if (g_mega_trace != nullptr && threadIdx.x == 0 && (id) < 48) {                                                   \
             unsigned long long t_;                                                                                       \
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                                        \
             g_mega_trace[blockIdx.x * 64 + (id)] = t_;                                                                   \
@@ -83,11 +89,35 @@ namespace {
     } while (0)
 #endif
 
+#ifdef GPTQ_TRACE
+// per-op counters of layer 2, team 0 of every CTA: ids 48 + 3 * op + {0: cycles in the op, 1: of which waiting for stages, 2: stages}
+#define OPTRACE_BEGIN(ring)                       \
+    const long long optr_t0 = clock64();          \
+    const long long optr_w0 = (ring).waited;      \
+    const int optr_s0 = (ring).stages
+#define OPTRACE_END(ring, layer, op)                                                                                   \
+    do {                                                                                                               \
+        if (g_mega_trace != nullptr && threadIdx.x == 0 && (layer) == 2) {                                              \
+            g_mega_trace[blockIdx.x * 64 + 48 + 3 * (op)] = (unsigned long long)(clock64() - optr_t0);                  \
+            g_mega_trace[blockIdx.x * 64 + 48 + 3 * (op) + 1] = (unsigned long long)((ring).waited - optr_w0);          \
+            g_mega_trace[blockIdx.x * 64 + 48 + 3 * (op) + 2] = (unsigned long long)((ring).stages - optr_s0);          \
+        }                                                                                                              \
+    } while (0)
+#else
+#define OPTRACE_BEGIN(ring) \
+    do {                    \
+    } while (0)
+#define OPTRACE_END(ring, layer, op) \
+    do {                             \
+    } while (0)
+#endif
+
 struct MatDesc {
-    const uint32_t* qw;
     const __half* sc;
     const uint32_t* qz;
     int gs_steps;  // k-steps per quantisation group (groupsize / 32)
+    int tmap;      // tensor-map class of qweight (0: N = 3H, 1: N = H, 2: N = I)
+    int chunk0;    // chunk coordinate of the matrix: (qweight - class base) / 128 bytes
 };
 struct LayerDesc {
     MatDesc qkv, o, gate, up, down;
@@ -117,10 +147,11 @@ struct MegaParams {
     float* acc_g;      // [I]
     float* acc_u;      // [I]
     float* acc_d;      // [H]
-    float* part;       // [teams][2][kRec]
+    float* part;       // [teams][2][kRec]  attention partial records
     float* rope_cs;    // [128]: cos[64], sin[64] of this step's position
     unsigned long long* bar;  // [0]: monotonic arrival counter of the grid barrier, [1]: its value when the previous launch ended
     LayerDesc layers[kMaxLayers];
+    CUtensorMap tmaps[6];  // [class]: 16-row boxes (a full stage), [3 + class]: 4-row boxes (one k-step)
 };
 
 // ---- work split ------------------------------------------------------------------------------------------------
@@ -129,8 +160,8 @@ __device__ __forceinline__ void team_range(unsigned T, unsigned U, unsigned nb, 
     a = (int)((T * U) / nb);  // T * U < 2^32 (checked by mega_plan)
     b = (int)(((T + 1) * U) / nb);
 }
-// k-steps of the stage that starts at step ks of a segment with `left` steps to go
-__device__ __forceinline__ int stage_steps(int ks, int gs_steps, int left) { return min(min(kStageSteps, gs_steps - ks % gs_steps), left); }
+// k-steps of the stage that starts `gpos` steps into its quantisation group, in a segment with `left` steps to go
+__device__ __forceinline__ int stage_steps(int gpos, int gs_steps, int left) { return min(min(kStageSteps, gs_steps - gpos), left); }
 
 // position of this step, clamped to the cache (the host rejects pos >= max_seq; the kernel must not write outside)
 __device__ __forceinline__ int step_pos(const MegaParams& p) { return min(max(p.positions[0], 0), p.max_seq - 1); }
@@ -143,9 +174,18 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 3, 512;" :::
 struct ProdRing {
     uint32_t ring, full, empty;
     int stage, use, nstages;
+#ifdef GPTQ_TRACE
+    long long blocked;  // cycles spent waiting for a free stage
+#endif
 };
 __device__ __forceinline__ uint32_t prod_acquire(ProdRing& r, uint32_t& bar) {
+#ifdef GPTQ_TRACE
+    const long long t0 = clock64();
+#endif
     if (r.use > 0) mbar_wait_backoff(r.empty + r.stage * 8, (r.use - 1) & 1u);  // the consumers released the previous use of this stage
+#ifdef GPTQ_TRACE
+    r.blocked += clock64() - t0;
+#endif
     bar = r.full + r.stage * 8;
     return r.ring + r.stage * kStageBytes;
 }
@@ -156,13 +196,18 @@ __device__ __forceinline__ void prod_advance(ProdRing& r) {
     }
 }
 
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst), "l"(tm), "r"(c0),
+                 "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+
 // weights of one matvec (NM matrices side by side: gate|up is one virtual matrix of 2 * N/256 slabs)
 template <int NM>
-__device__ void produce_matvec(ProdRing& r, const MatDesc* const (&md)[NM], int K, int N, unsigned T, unsigned nb) {
+__device__ void produce_matvec(ProdRing& r, const MegaParams& p, const MatDesc* const (&md)[NM], int K, int N, unsigned T, unsigned nb) {
     const int nk = K / 32, nslab = N / kSlabCols;
     int u, u1;
     team_range(T, (unsigned)(NM * nslab) * nk, nb, u, u1);
-    const size_t row_bytes = (size_t)N * 4;
 #pragma unroll 1
     while (u < u1) {
         const int slab_v = u / nk;
@@ -171,23 +216,30 @@ __device__ void produce_matvec(ProdRing& r, const MatDesc* const (&md)[NM], int 
         const int mi = (NM > 1 && slab_v >= nslab) ? 1 : 0;
         const int slab = slab_v - mi * nslab;
         const MatDesc& m = *md[mi];
-        const uint8_t* wbase = reinterpret_cast<const uint8_t*>(m.qw) + (size_t)slab * (kSlabCols * 4);
+        const int chunk = m.chunk0 + slab * (kSlabCols / 32);
         int left = nseg;
+        int g = ks / m.gs_steps, gpos = ks - g * m.gs_steps;  // group of step ks and the position inside it
 #pragma unroll 1
         while (left > 0) {
-            const int n = stage_steps(ks, m.gs_steps, left);
+            const int n = stage_steps(gpos, m.gs_steps, left);
             uint32_t bar;
             const uint32_t dst = prod_acquire(r, bar);
-            mbar_expect_tx(bar, n * 4096 + 640);
-            const uint8_t* src = wbase + (size_t)(ks * 4) * row_bytes;
-#pragma unroll 4
-            for (int rr = 0; rr < 4 * n; ++rr) bulk_copy_g2s(dst + rr * kRowPitch, src + rr * row_bytes, 1024, bar);
-            const int g = ks / m.gs_steps;
+            mbar_expect_tx(bar, n * kStepBytes + 640);
+            if (n == kStageSteps) {
+                tma_load_3d(dst, &p.tmaps[m.tmap], 0, ks * 4, chunk, bar);
+            } else {
+                for (int j = 0; j < n; ++j) tma_load_3d(dst + j * kStepBytes, &p.tmaps[3 + m.tmap], 0, (ks + j) * 4, chunk, bar);
+            }
             bulk_copy_g2s(dst + kScaleOff, m.sc + (size_t)g * N + slab * kSlabCols, 512, bar);
             bulk_copy_g2s(dst + kZeroOff, m.qz + (size_t)g * (N >> 3) + slab * (kSlabCols / 8), 128, bar);
             prod_advance(r);
             ks += n;
             left -= n;
+            gpos += n;
+            if (gpos == m.gs_steps) {
+                gpos = 0;
+                ++g;
+            }
         }
         u += nseg;
     }
@@ -236,23 +288,26 @@ __device__ void producer_loop(const MegaParams& p, ProdRing r, unsigned T, unsig
         const LayerDesc& L = p.layers[l];
         {
             const MatDesc* const md[1] = {&L.qkv};
-            produce_matvec<1>(r, md, p.H, 3 * p.H, T, nb);
+            produce_matvec<1>(r, p, md, p.H, 3 * p.H, T, nb);
         }
         produce_kv(r, p, l, T, nb);
         {
             const MatDesc* const md[1] = {&L.o};
-            produce_matvec<1>(r, md, p.H, p.H, T, nb);
+            produce_matvec<1>(r, p, md, p.H, p.H, T, nb);
         }
         {
             const MatDesc* const md[2] = {&L.gate, &L.up};
-            produce_matvec<2>(r, md, p.H, p.I, T, nb);
+            produce_matvec<2>(r, p, md, p.H, p.I, T, nb);
         }
         {
             const MatDesc* const md[1] = {&L.down};
-            produce_matvec<1>(r, md, p.I, p.H, T, nb);
+            produce_matvec<1>(r, p, md, p.I, p.H, T, nb);
         }
     }
     produce_lm_head(r, p, T, nb);
+#ifdef GPTQ_TRACE
+    if (g_mega_trace != nullptr && (T & 1) == 0) g_mega_trace[(T / kTeams) * 64 + 63] = (unsigned long long)r.blocked;
+#endif
 }
 
 // ---- consumer side of the ring -----------------------------------------------------------------------------------------
@@ -261,9 +316,20 @@ struct ConsRing {
     uint32_t tile, bar;   // current stage
     uint32_t parity;
     int left, nstages;
+#ifdef GPTQ_TRACE
+    long long waited;  // cycles spent waiting for stages to land
+    int stages;
+#endif
 };
-__device__ __forceinline__ uint32_t cons_wait(const ConsRing& c) {
+__device__ __forceinline__ uint32_t cons_wait(ConsRing& c) {
+#ifdef GPTQ_TRACE
+    const long long t0 = clock64();
+#endif
     mbar_wait(c.bar, c.parity);
+#ifdef GPTQ_TRACE
+    c.waited += clock64() - t0;
+    ++c.stages;
+#endif
     return c.tile;
 }
 // every lane of the warp has finished reading the stage
@@ -292,7 +358,9 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
         do {
             asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(bar) : "memory");
         } while (v < target);
-        fence_acq_rel_gpu();  // also drops this SM's stale L1 lines of data other CTAs have rewritten
+#ifdef GPTQ_BARRIER_FENCE
+        fence_acq_rel_gpu();
+#endif
     }
     cta_sync();
 }
@@ -427,14 +495,20 @@ __device__ void stage_norm(const MegaParams& p, const __half* src, const float* 
                 const float2 wf = __half22float2(u32_as_h2(wv[j]));
                 o[j] = h2_as_u32(__floats2half2_rn(__fmul_rn(__fmul_rn(xf[2 * j], rstd), wf.x), __fmul_rn(__fmul_rn(xf[2 * j + 1], rstd), wf.y)));
             }
-            *reinterpret_cast<uint4*>(xs + c * 8) = PLAIN ? make_uint4(o[0], o[1], o[2], o[3]) : perm8(o[0], o[1], o[2], o[3]);
+            if constexpr (PLAIN) {
+                *reinterpret_cast<uint4*>(xs + c * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            } else {
+                const uint4 pv = perm8(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(xs + c * 8) = pv;
+                // per-step sums of the staged x: the 4 runs of a k-step sit in 4 consecutive lanes (c < nch is uniform per warp)
+                float v = run_sum(pv);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((c & 3) == 0) xsum[c >> 2] = v;
+            }
         }
     }
     cta_sync();
-    if constexpr (!PLAIN) {
-        compute_xsum(xs, H / 32, xsum, tid, kConsumers);
-        cta_sync();
-    }
 }
 
 // ---- matvec consumer ---------------------------------------------------------------------------------------------------
@@ -446,7 +520,8 @@ __device__ __forceinline__ void mma_16816_z(float (&d)[4], uint32_t a0, uint32_t
 
 // the four A registers (k-pairs (0,4), (1,5), (2,6), (3,7)) of one packed word
 __device__ __forceinline__ void nibble_regs(uint32_t q, uint32_t (&a)[4]) {
-    const uint32_t q8 = q >> 8;
+    uint32_t q8;  // q >> 8 as a multiply-high: IMAD.HI runs on the FMA pipe, the masks below saturate the integer ALU pipe
+    asm("mul.hi.u32 %0, %1, 0x01000000;" : "=r"(q8) : "r"(q));
     if (kSubnormal) {  // masked in place: fp16 subnormals n * 2^-24 and 16 n * 2^-24
         a[0] = q & 0x000f000fu;
         a[1] = q & 0x00f000f0u;
@@ -488,7 +563,43 @@ struct TeamCtx {
     __half* xseg;              // this team's half of the xs buffer (per-segment inputs of O and D)
     float* xsum_seg;
     uint8_t* scratch;          // kTeamScratch bytes
+    const unsigned short* mt_rec;  // merge table (per CTA): entry e = team + head -> attention record index (0xffff: none)
+    const unsigned* mt_range;      // [n_heads]: entry range e0 | e1 << 16 of the head
 };
+
+// Which attention partial records belong to which head: a function of the step's position only, computed once per launch by
+// every CTA into its shared memory.  Entry index e = Tt + head is unique (consecutive heads share at most one team).
+__device__ void build_merge_table(const MegaParams& p, unsigned nb, unsigned short* mt_rec, unsigned* mt_range) {
+    const int tid = threadIdx.x;
+    const int Tlen = step_pos(p) + 1;
+    const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
+    const unsigned Ua = (unsigned)(p.n_heads * upb);
+    const int n_ent = (int)nb + p.n_heads;
+    for (int e = tid; e < n_ent; e += kConsumers) mt_rec[e] = 0xffffu;
+    cta_sync();
+    for (unsigned Tt = tid; Tt < nb; Tt += kConsumers) {
+        int a, b;
+        team_range(Tt, Ua, nb, a, b);
+        if (a < b) {
+            const int hf = a / upb, hl = (b - 1) / upb;  // first / last head of the team (at most two heads)
+            mt_rec[Tt + hf] = (unsigned short)(Tt * 2);
+            if (hl != hf) mt_rec[Tt + hl] = (unsigned short)(Tt * 2 + 1);
+        }
+    }
+    for (int hd = tid; hd < p.n_heads; hd += kConsumers) {
+        // teams that can hold units of the head: from the one whose range reaches unit hd * upb to the one holding its last unit
+        const unsigned t0 = ((unsigned)(hd * upb) * nb) / Ua;
+        unsigned t1 = ((unsigned)((hd + 1) * upb - 1) * nb) / Ua;
+        int a, b;
+        team_range(t1, Ua, nb, a, b);
+        while (b <= (hd + 1) * upb - 1 && t1 + 1 < nb) {  // floor(u * nb / U) can fall one team short of the owner of unit u
+            ++t1;
+            team_range(t1, Ua, nb, a, b);
+        }
+        mt_range[hd] = (t0 + hd) | ((t1 + hd + 1) << 16);
+    }
+    cta_sync();
+}
 
 // One matvec op for this team: consume the stages of its unit range from the ring, RED the results.
 // NM = 2: gate|up as one virtual matrix (out0 = gate accumulators, out1 = up accumulators).
@@ -499,10 +610,18 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
     const int nk = K / 32, nslab = N / kSlabCols;
     int u, u_end;
     team_range(tc.T, (unsigned)(NM * nslab) * nk, tc.nb, u, u_end);
-    const uint32_t lane_w = (uint32_t)(t * kRowPitch + tc.wt * 128 + g * 16);     // this lane's 16 B in row t of a k-step
-    const uint32_t lane_s = (uint32_t)(kScaleOff + (tc.wt * 32 + 4 * g) * 2);      // its 4 scales
-    const uint32_t lane_z = (uint32_t)(kZeroOff + (tc.wt * 4 + (g >> 1)) * 4);     // the qzeros word holding its 4 zeros
-    const int zshift = (g & 1) * 16;
+    // MMA row g of this lane carries the 4 columns of 16-byte unit cg of the warp's 128-byte chunk; cg is chosen so that the
+    // swizzled units (unit ^ row) of a quarter-warp (g in {2q, 2q+1}, t = 0..3) are 8 distinct bank groups
+    const int cg = (g >> 1) | ((g & 1) << 2);
+    const int col_l = 4 * cg + t;  // the column (of the warp's 32) this lane finishes in the epilogue
+    // 16-row box [chunk][row][128 B]: row 4j + t of chunk wt, unit cg ^ ((4j + t) & 7)
+    const uint32_t lane_a0 = (uint32_t)((tc.wt * 16 + t) * 128 + ((cg ^ t) * 16));       // even k-steps of the stage
+    const uint32_t lane_a1 = (uint32_t)((tc.wt * 16 + t) * 128 + ((cg ^ t ^ 4) * 16));   // odd k-steps
+    // 4-row boxes (one per k-step, 4 KB apart) [chunk][row][128 B]: line wt * 4 + t
+    const uint32_t lane_b = (uint32_t)((tc.wt * 4 + t) * 128 + ((cg ^ (4 * (tc.wt & 1) + t)) * 16));
+    const uint32_t lane_s = (uint32_t)(kScaleOff + (tc.wt * 32 + col_l) * 2);      // scale of its column
+    const uint32_t lane_z = (uint32_t)(kZeroOff + (tc.wt * 4 + (cg >> 1)) * 4);    // the qzeros word holding its zero
+    const int zshift = (cg & 1) * 16 + t * 4;
     const float unit = kSubnormal ? 16777216.0f : 1.0f;  // the accumulators are in units of 2^-24
 
 #pragma unroll 1
@@ -511,7 +630,7 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
         const int ks0 = u - slab_v * nk;
         const int nseg = min(nk - ks0, u_end - u);
         const int mi = (NM > 1 && slab_v >= nslab) ? 1 : 0;
-        float* outp = (mi ? out1 : out0) + (slab_v - mi * nslab) * kSlabCols + tc.wt * 32 + 4 * g;
+        float* outp = (mi ? out1 : out0) + (slab_v - mi * nslab) * kSlabCols + tc.wt * 32 + col_l;
 
         uint32_t xaddr;
         const float* xsum;
@@ -533,34 +652,46 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
                     const uint32_t o3 = h2_as_u32(__floats2half2_rn(swiglu(g1.z, u1.z), swiglu(g1.w, u1.w)));
                     *reinterpret_cast<uint4*>(tc.xseg + c * 8) = perm8(o0, o1, o2, o3);
                 }
-            } else {  // attention output: one thread per feature merges the partial records of its head
-                const int Tlen = step_pos(p) + 1;
-                const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
-                const unsigned Ua = (unsigned)(p.n_heads * upb);
+            } else {
+                // attention output: softmax-merge of the partial records (m, l, o[128]) the teams wrote for the head; which records
+                // belong to a head is in the CTA's merge table (build_merge_table, once per launch).  All loads are independent.
                 for (int e = tc.ttid; e < nseg * 32; e += kTeamThreads) {
                     int k = kbeg + e;
                     if constexpr (ACT) {
                         if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
                     }
                     const int head = k / kHD, d = k - head * kHD;
-                    const int hu0 = head * upb, hu1 = hu0 + upb;
-                    // teams whose unit range meets [hu0, hu1)
-                    const unsigned Tlo = ((unsigned)hu0 * tc.nb) / Ua;
-                    float M = -INFINITY, Lsum = 0.f, O = 0.f;
-                    for (unsigned Tt = Tlo; Tt < tc.nb; ++Tt) {
-                        int a, b;
-                        team_range(Tt, Ua, tc.nb, a, b);
-                        if (a >= hu1) break;
-                        if (b <= hu0 || a >= b) continue;
-                        const float* rec = p.part + ((size_t)Tt * 2 + (a >= hu0 ? 0 : 1)) * kRec;
-                        const float m = ld_cg(rec), lv = ld_cg(rec + 1), ov = ld_cg(rec + 4 + d);
-                        const float Mn = fmaxf(M, m);
-                        const float wa = (M == -INFINITY) ? 0.f : expf(M - Mn), wb = (m == -INFINITY) ? 0.f : expf(m - Mn);
-                        Lsum = Lsum * wa + lv * wb;
-                        O = O * wa + ov * wb;
-                        M = Mn;
+                    const unsigned range = tc.mt_range[head];
+                    const int e0 = (int)(range & 0xffffu), e1 = (int)(range >> 16);
+                    float M = -INFINITY, Ls = 0.f, O = 0.f;
+                    constexpr int kBatch = 12;  // records fetched per round trip (a 7B head has at most 12)
+#pragma unroll 1
+                    for (int eb = e0; eb < e1; eb += kBatch) {
+                        float mv[kBatch], lv[kBatch], ov[kBatch];
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i) {  // all loads of the batch are in flight together
+                            const unsigned ri = (eb + i < e1) ? (unsigned)tc.mt_rec[eb + i] : 0xffffu;
+                            const float* rc = p.part + (size_t)(ri == 0xffffu ? 0u : ri) * kRec;
+                            const float m = ld_cg(rc), l = ld_cg(rc + 1), o = ld_cg(rc + 4 + d);
+                            mv[i] = ri == 0xffffu ? -INFINITY : m;
+                            lv[i] = ri == 0xffffu ? 0.f : l;
+                            ov[i] = ri == 0xffffu ? 0.f : o;
+                        }
+                        float Mb = M;
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i) Mb = fmaxf(Mb, mv[i]);
+                        const float w0 = (M == -INFINITY) ? 0.f : expf(M - Mb);
+                        Ls *= w0;
+                        O *= w0;
+#pragma unroll
+                        for (int i = 0; i < kBatch; ++i) {
+                            const float w = (mv[i] == -INFINITY) ? 0.f : expf(mv[i] - Mb);
+                            Ls = fmaf(lv[i], w, Ls);
+                            O = fmaf(ov[i], w, O);
+                        }
+                        M = Mb;
                     }
-                    __half hv = __float2half_rn(O / Lsum);
+                    __half hv = __float2half_rn(O / Ls);
                     const int j8 = e & 7;
                     if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
                     tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
@@ -573,18 +704,18 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
             xsum = tc.xsum_seg;
         }
 
-        float tot[4] = {0.f, 0.f, 0.f, 0.f};
-        int ks = ks0, left = nseg;
+        float tot = 0.f;  // lane (g, t) finishes column 4g + t of the warp's stripe
+        int left = nseg, gpos = ks0 % gs_steps;
 #pragma unroll 1
         while (left > 0) {
-            const int n = stage_steps(ks, gs_steps, left);
+            const int n = stage_steps(gpos, gs_steps, left);
             const uint32_t st = cons_wait(ring);
             float acc0[4], acc1[4];
             float xs4;
             if (n == kStageSteps) {
                 uint4 q[4], xf[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) q[j] = lds128(st + lane_w + j * 4 * kRowPitch);
+                for (int j = 0; j < 4; ++j) q[j] = lds128(st + j * 512 + ((j & 1) ? lane_a1 : lane_a0));
 #pragma unroll
                 for (int j = 0; j < 4; ++j) xf[j] = lds128(xaddr + j * 64);
                 step_mma<true>(q[0], xf[0], acc0, acc1);
@@ -594,41 +725,35 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
                 xs4 = (xsum[0] + xsum[1]) + (xsum[2] + xsum[3]);
             } else {
                 {
-                    const uint4 q = lds128(st + lane_w), xf = lds128(xaddr);
+                    const uint4 q = lds128(st + lane_b), xf = lds128(xaddr);
                     step_mma<true>(q, xf, acc0, acc1);
                     xs4 = xsum[0];
                 }
 #pragma unroll 1
                 for (int j = 1; j < n; ++j) {
-                    const uint4 q = lds128(st + lane_w + j * 4 * kRowPitch), xf = lds128(xaddr + j * 64);
+                    const uint4 q = lds128(st + lane_b + j * kStepBytes), xf = lds128(xaddr + j * 64);
                     step_mma<false>(q, xf, acc0, acc1);
                     xs4 += xsum[j];
                 }
             }
-            // group epilogue: tot += s * (acc * unit - z * sum(x))   (z = stored zero + 1, quant/quant_linear.py:120-121)
+            // group epilogue: tot += s * (acc * unit - z * sum(x))   (z = stored zero + 1, quant/quant_linear.py:120-121).
+            // All four t lanes hold the same four column sums (the batch columns of B are copies): lane t finishes column 4g + t.
             {
-                uint2 sv;
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(sv.x), "=r"(sv.y) : "r"(st + lane_s));
-                uint32_t zw;
+                uint32_t sh, zw;
+                asm volatile("ld.shared.u16 %0, [%1];" : "=r"(sh) : "r"(st + lane_s));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(zw) : "r"(st + lane_z));
-                zw >>= zshift;
-                const float2 s01 = __half22float2(u32_as_h2(sv.x)), s23 = __half22float2(u32_as_h2(sv.y));
-                const float sc[4] = {s01.x, s01.y, s23.x, s23.y};
-                const float av[4] = {acc0[0], acc0[2], acc1[0], acc1[2]};  // batch row 0 of columns 4g .. 4g+3
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float z = (float)(((zw >> (4 * c)) & 15u) + 1u);
-                    tot[c] = fmaf(sc[c], fmaf(av[c], unit, -z * xs4), tot[c]);
-                }
+                const float a = (t & 2) ? ((t & 1) ? acc1[2] : acc1[0]) : ((t & 1) ? acc0[2] : acc0[0]);
+                const float z = (float)(((zw >> zshift) & 15u) + 1u);
+                tot = fmaf(__half2float(__ushort_as_half((unsigned short)sh)), fmaf(a, unit, -z * xs4), tot);
             }
             cons_release(ring, lane);
             xaddr += n * 64;
             xsum += n;
-            ks += n;
             left -= n;
+            gpos += n;
+            if (gpos == gs_steps) gpos = 0;
         }
-        // all four t lanes hold the same sums: lane t == 0 publishes them
-        if (t == 0) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(outp), "f"(tot[0]), "f"(tot[1]), "f"(tot[2]), "f"(tot[3]) : "memory");
+        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(outp), "f"(tot) : "memory");  // the warp's 32 columns: one 128-byte line
         u += nseg;
     }
 }
@@ -641,11 +766,11 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
     const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
     int u, u_end;
     team_range(tc.T, (unsigned)(p.n_heads * upb), tc.nb, u, u_end);
-    float* q_s = reinterpret_cast<float*>(tc.scratch);                   // [128]
+    float* red_o = reinterpret_cast<float*>(tc.scratch);                 // [8][128]  end of a segment
+    float* red_ml = reinterpret_cast<float*>(tc.scratch + 4096);         // [8][2]
+    float* q_s = reinterpret_cast<float*>(tc.scratch);                   // [128]     start of a segment (aliases red_o)
     __half* knew = reinterpret_cast<__half*>(tc.scratch + 512);          // [128]
     __half* vnew = knew + kHD;                                          // [128]
-    float* red_ml = reinterpret_cast<float*>(tc.scratch + 1024);         // [8][2]
-    float* red_o = reinterpret_cast<float*>(tc.scratch + 1024 + 64);     // [8][128]
     const int ttid = tc.ttid, lane = tc.lane, grp = ttid >> 3, j = ttid & 7;  // 32 groups of 8 lanes: group = key, lane j owns dims 8j..8j+7 and 64+8j..64+8j+7
     const int ub_new = pos / kKeysPerUnit;  // the unit that holds this step's key
     __half* kc_l = p.k_cache + layer * p.layer_stride;
@@ -660,7 +785,7 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
         if (ttid < kHD) {
             const int i = ttid & 63;
             const bool hi = ttid >= 64;
-            const float c = p.rope_cs[i], s = p.rope_cs[64 + i];
+            const float c = ld_cg(p.rope_cs + i), s = ld_cg(p.rope_cs + 64 + i);
             const float* aq = p.acc_qkv + head * kHD;
             const float qx = __half2float(__float2half_rn(ld_cg(aq + i))), qy = __half2float(__float2half_rn(ld_cg(aq + i + 64)));  // the qkv projection output is fp16
             const float qr = hi ? __fadd_rn(__fmul_rn(qx, s), __fmul_rn(qy, c)) : __fsub_rn(__fmul_rn(qx, c), __fmul_rn(qy, s));
@@ -738,6 +863,7 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
             }
             cons_release(ring, lane);
         }
+        team_sync(tc.team);  // every warp has read q_s and passed the patch: the merge buffers (which alias q_s / knew / vnew) may be written
         // merge the 4 key groups of the warp (lanes xor 8, 16), then the 8 warps through shared memory
 #pragma unroll
         for (int sh = 8; sh <= 16; sh <<= 1) {
@@ -853,15 +979,18 @@ __device__ void run_lm_head(const MegaParams& p, ConsRing& ring, const TeamCtx& 
 
 template <bool ACT>
 __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __grid_constant__ MegaParams p) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(16) uint8_t smem_dyn[];
+    uint8_t* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);  // TMA swizzle atoms: 1 KB aligned stages (1 KB of slack is allocated)
     __shared__ float red_s[kConsumerWarps];
     __shared__ __align__(8) unsigned long long bars_s[kTeams][2 * kMaxStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // smem: [team 0 ring][team 1 ring][xs: H halves][xsum: H/32 floats][tmp / team scratch]
+    // smem (1 KB aligned): [team 0 ring][team 1 ring][xs: H halves][xsum: H/32 floats][merge table][tmp / team scratch]
     const uint32_t ring_bytes = (uint32_t)p.n_stages * kStageBytes;
     __half* xs = reinterpret_cast<__half*>(smem_raw + kTeams * ring_bytes);
     float* xsum = reinterpret_cast<float*>(xs + p.H);
-    uint8_t* tmp_raw = reinterpret_cast<uint8_t*>(xsum + p.H / 32);
+    unsigned* mt_range = reinterpret_cast<unsigned*>(xsum + p.H / 32);                     // [n_heads]
+    unsigned short* mt_rec = reinterpret_cast<unsigned short*>(mt_range + p.n_heads);      // [teams + n_heads]
+    uint8_t* tmp_raw = reinterpret_cast<uint8_t*>(mt_rec + (gridDim.x * kTeams + p.n_heads));
     tmp_raw += (16 - (reinterpret_cast<uintptr_t>(tmp_raw) & 15)) & 15;
     __half* tmp = reinterpret_cast<__half*>(tmp_raw);
 
@@ -886,6 +1015,9 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
             r.stage = 0;
             r.use = 0;
             r.nstages = p.n_stages;
+#ifdef GPTQ_TRACE
+            r.blocked = 0;
+#endif
             producer_loop(p, r, blockIdx.x * kTeams + tm, nb);
         }
         return;
@@ -900,6 +1032,8 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     tc.xseg = xs + tc.team * (p.H / 2);
     tc.xsum_seg = xsum + tc.team * (p.H / 64);
     tc.scratch = tmp_raw + tc.team * kTeamScratch;
+    tc.mt_rec = mt_rec;
+    tc.mt_range = mt_range;
     ConsRing ring;
     ring.ring = smem_u32(smem_raw) + tc.team * ring_bytes;
     ring.full = smem_u32(&bars_s[tc.team][0]);
@@ -908,6 +1042,10 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     ring.parity = 0;
     ring.left = p.n_stages;
     ring.nstages = p.n_stages;
+#ifdef GPTQ_TRACE
+    ring.waited = 0;
+    ring.stages = 0;
+#endif
 
     unsigned long long gen;  // barrier target (meaningful in thread 0): the counter value when this launch began
     {
@@ -917,6 +1055,8 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar + 1) : "memory");
         gen = v;
     }
+
+    build_merge_table(p, nb, mt_rec, mt_range);
 
     // this step's RoPE angles (quant/fused_attn.py:43,91): freq_i = exp(i * inv_base) * pos
     if (blockIdx.x == 0 && tid < 64) {
@@ -940,19 +1080,31 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         cur ^= 1;
         zero_slice(p.acc_g, p.I);  // last read by the previous layer's D
         zero_slice(p.acc_u, p.I);
-        run_matvec<1, X_FULL>(p, ring, tc, L.qkv.gs_steps, p.H, 3 * p.H, p.acc_qkv, nullptr, xs, xsum);
+        {
+            OPTRACE_BEGIN(ring);
+            run_matvec<1, X_FULL>(p, ring, tc, L.qkv.gs_steps, p.H, 3 * p.H, p.acc_qkv, nullptr, xs, xsum);
+            OPTRACE_END(ring, l, 0);
+        }
         MTRACE(l * 12 + 2);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 3);
         // ---- A ----
         zero_slice(p.acc_d, p.H);  // last read by this layer's Q
-        run_attention(p, ring, tc, l);
+        {
+            OPTRACE_BEGIN(ring);
+            run_attention(p, ring, tc, l);
+            OPTRACE_END(ring, l, 1);
+        }
         MTRACE(l * 12 + 4);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 5);
         // ---- O ----
         zero_slice(p.acc_qkv, 3 * p.H);
-        run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.H, p.H, p.acc_o, nullptr, xs, xsum, L.o_perm);
+        {
+            OPTRACE_BEGIN(ring);
+            run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.H, p.H, p.acc_o, nullptr, xs, xsum, L.o_perm);
+            OPTRACE_END(ring, l, 2);
+        }
         MTRACE(l * 12 + 6);
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 7);
@@ -960,13 +1112,21 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         stage_norm<ACT, false>(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, xsum, tmp, red_s, L.mlp_perm);
         cur ^= 1;
         MTRACE(l * 12 + 8);
-        run_matvec<2, X_FULL>(p, ring, tc, L.gate.gs_steps, p.H, p.I, p.acc_g, p.acc_u, xs, xsum);
+        {
+            OPTRACE_BEGIN(ring);
+            run_matvec<2, X_FULL>(p, ring, tc, L.gate.gs_steps, p.H, p.I, p.acc_g, p.acc_u, xs, xsum);
+            OPTRACE_END(ring, l, 3);
+        }
         MTRACE(l * 12 + 9);
         grid_barrier(p.bar, gen);
         // ---- D ----
         zero_slice(p.acc_o, p.H);
         MTRACE(l * 12 + 10);
-        run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.acc_d, nullptr, xs, xsum);
+        {
+            OPTRACE_BEGIN(ring);
+            run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.acc_d, nullptr, xs, xsum);
+            OPTRACE_END(ring, l, 4);
+        }
         MTRACE(l * 12 + 11);
         grid_barrier(p.bar, gen);
         resid_src = p.resid[cur];
@@ -985,7 +1145,7 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
             float best = -INFINITY;
             int idx = 0x7fffffff;
             for (int i = tid; i < p.V; i += kConsumers) {
-                const float v = __half2float(p.logits[i]);
+                const float v = __half2float(ld_cg_h(p.logits + i));  // written by other CTAs
                 if (v > best || (v == best && i < idx)) {
                     best = v;
                     idx = i;
@@ -1021,6 +1181,22 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
 
 inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// 3-D view of packed matrices with row stride N * 4 bytes: {32 words (128 B), packed rows, 128-byte chunks}, box 32 x box_rows x 8
+// (= box_rows rows of a 256-column slab), 128-byte swizzle.  cuTensorMapEncodeTiled comes through the runtime's driver entry
+// point (libcuda is not linked: the library must load without a driver).
+bool encode_weight_map(CUtensorMap* tm, const void* base, int rows, uint64_t chunks, int N, int box_rows) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || fn == nullptr) return false;
+    const auto encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    const cuuint64_t dims[3] = {32, (cuuint64_t)rows, (cuuint64_t)chunks};  // innermost first
+    const cuuint64_t strides[2] = {(cuuint64_t)N * 4, 128};                 // bytes: packed row, chunk
+    const cuuint32_t box[3] = {32, (cuuint32_t)box_rows, (cuuint32_t)(kSlabCols / 32)};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // device properties that shape the launch (queried per call: no cached global state)
 struct MegaPlan {
     int grid, n_stages, lm_rows;
@@ -1029,16 +1205,18 @@ struct MegaPlan {
 
 // Shared-memory plan for this model on a device with `sms` SMs and `smem_max` bytes of opt-in shared memory per block;
 // returns false if the shape does not fit the kernel's staging buffers.
-bool mega_plan(const gptq_llama_model& m, int sms, size_t smem_max, MegaPlan& pl) {
+bool mega_plan(const gptq_llama_model& m, int sms, size_t smem_max, size_t smem_static, MegaPlan& pl) {
     const int H = m.hidden, I = m.intermediate;
-    const size_t fixed = (size_t)H * 2 + (size_t)(H / 32) * 4 + 16 + max((size_t)H * 2, (size_t)kTeams * kTeamScratch);
-    if (smem_max < fixed + 1024) return false;
-    int st = (int)((smem_max - fixed - 1024) / ((size_t)kTeams * kStageBytes));  // 1 KB: static shared memory of the kernel
+    const size_t table = (size_t)m.n_heads * 4 + (size_t)(sms * kTeams + m.n_heads) * 2;  // attention merge table
+    const size_t fixed = (size_t)H * 2 + (size_t)(H / 32) * 4 + table + 16 + max((size_t)H * 2, (size_t)kTeams * kTeamScratch);
+    const size_t other = fixed + smem_static + 1024;  // + the kernel's static shared memory + 1 KB alignment slack of the rings
+    if (smem_max < other) return false;
+    int st = (int)((smem_max - other) / ((size_t)kTeams * kStageBytes));
     st = min(st, kMaxStages);
     if (st < 2) return false;
     pl.grid = sms;
     pl.n_stages = st;
-    pl.smem = fixed + (size_t)kTeams * st * kStageBytes;
+    pl.smem = fixed + 1024 + (size_t)kTeams * st * kStageBytes;
     pl.lm_rows = max(1, kLmStageBytes / (H * 2));
     if ((size_t)pl.lm_rows * H * 2 > (size_t)kStageBytes) return false;
     if ((size_t)2 * pl.lm_rows * kTeamWarps * 4 > (size_t)kTeamScratch) return false;
@@ -1089,8 +1267,13 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
         return cudaErrorInvalidDevice;
+    bool any_perm = false;
+    for (int l = 0; l < m.n_layers; ++l) any_perm = any_perm || m.layers[l].qkv_perm != nullptr || m.layers[l].o_perm != nullptr || m.layers[l].mlp_perm != nullptr;
+    auto kernel = any_perm ? llama_decode_mega_kernel<true> : llama_decode_mega_kernel<false>;
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, kernel) != cudaSuccess) return cudaErrorInvalidDeviceFunction;
     MegaPlan pl;
-    if (sms * kTeams > 1024 || !mega_plan(m, sms, (size_t)smem_optin, pl)) return cudaErrorInvalidConfiguration;
+    if (sms * kTeams > 1024 || !mega_plan(m, sms, (size_t)smem_optin, fa.sharedSizeBytes, pl)) return cudaErrorInvalidConfiguration;
 
     MegaParams p{};
     p.n_layers = m.n_layers; p.H = m.hidden; p.I = m.intermediate; p.V = m.vocab; p.n_heads = m.n_heads;
@@ -1126,22 +1309,50 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     p.part = reinterpret_cast<float*>(take((size_t)1024 * 2 * kRec * 4));
     p.rope_cs = reinterpret_cast<float*>(take(128 * 4));
     p.bar = reinterpret_cast<unsigned long long*>(take(256));
+    // One tensor map per row stride serves every layer: class 0 = qkv (N = 3H), 1 = o and down (N = H), 2 = gate and up (N = I).
+    // Its base is the lowest qweight address of the class; a matrix is addressed through the chunk coordinate (128-byte units).
+    const int classN[3] = {3 * m.hidden, m.hidden, m.intermediate};
+    uintptr_t base[3] = {UINTPTR_MAX, UINTPTR_MAX, UINTPTR_MAX}, top[3] = {0, 0, 0};
+    int rows_max[3] = {0, 0, 0};
+    auto visit = [&](const gptq_qweight& w, int c) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(w.qweight);
+        base[c] = a < base[c] ? a : base[c];
+        top[c] = a > top[c] ? a : top[c];
+        rows_max[c] = max(rows_max[c], w.K / 8);
+    };
+    for (int l = 0; l < m.n_layers; ++l) {
+        const gptq_llama_layer& ly = m.layers[l];
+        visit(ly.qkv, 0); visit(ly.o, 1); visit(ly.down, 1); visit(ly.gate, 2); visit(ly.up, 2);
+    }
+    for (int c = 0; c < 3; ++c) {
+        if ((base[c] & 127) != 0) return cudaErrorInvalidConfiguration;
+        const uint64_t chunks = (uint64_t)(top[c] - base[c]) / 128 + (uint64_t)classN[c] / 32;
+        if (chunks >= (1ull << 31)) return cudaErrorInvalidConfiguration;
+        for (int v = 0; v < 2; ++v)
+            if (!encode_weight_map(&p.tmaps[3 * v + c], reinterpret_cast<const void*>(base[c]), rows_max[c], chunks, classN[c], v == 0 ? 4 * kStageSteps : 4))
+                return cudaErrorNotSupported;
+    }
     bool act = false;  // any act-order gather: the ACT instantiation (the plain one carries no trace of the feature)
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
-        auto md = [](const gptq_qweight& w) {
+        bool aligned = true;
+        auto md = [&](const gptq_qweight& w, int c) {
             MatDesc d;
-            d.qw = reinterpret_cast<const uint32_t*>(w.qweight);
             d.sc = reinterpret_cast<const __half*>(w.scales);
             d.qz = reinterpret_cast<const uint32_t*>(w.qzeros);
             d.gs_steps = w.groupsize / 32;
+            d.tmap = c;
+            const uintptr_t delta = reinterpret_cast<uintptr_t>(w.qweight) - base[c];
+            aligned = aligned && (delta % 128 == 0);
+            d.chunk0 = (int)(delta / 128);
             return d;
         };
-        p.layers[l].qkv = md(ly.qkv);
-        p.layers[l].o = md(ly.o);
-        p.layers[l].gate = md(ly.gate);
-        p.layers[l].up = md(ly.up);
-        p.layers[l].down = md(ly.down);
+        p.layers[l].qkv = md(ly.qkv, 0);
+        p.layers[l].o = md(ly.o, 1);
+        p.layers[l].gate = md(ly.gate, 2);
+        p.layers[l].up = md(ly.up, 2);
+        p.layers[l].down = md(ly.down, 1);
+        if (!aligned) return cudaErrorInvalidConfiguration;
         p.layers[l].input_norm = reinterpret_cast<const __half*>(ly.input_norm);
         p.layers[l].post_norm = reinterpret_cast<const __half*>(ly.post_norm);
         p.layers[l].qkv_perm = ly.qkv_perm;
@@ -1149,7 +1360,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
         p.layers[l].mlp_perm = ly.mlp_perm;
         act = act || ly.qkv_perm != nullptr || ly.o_perm != nullptr || ly.mlp_perm != nullptr;
     }
-    auto kernel = act ? llama_decode_mega_kernel<true> : llama_decode_mega_kernel<false>;
+    (void)act;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     int occ = 0;

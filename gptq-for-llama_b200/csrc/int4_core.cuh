@@ -71,6 +71,11 @@ __device__ __forceinline__ float4 ld_cg4(const float* p) {
     asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ __half ld_cg_h(const __half* p) {
+    unsigned short r;
+    asm volatile("ld.global.cg.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return __ushort_as_half(r);
+}
 __device__ __forceinline__ uint4 ld_cg_u4(const void* p) {
     uint4 r;
     asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));

@@ -61,13 +61,16 @@ class QLayerWeights:
 def random_qlayer(K, N, bits, groupsize, device, gen, act_order=False):
     """Synthetic packed layer (SURVEY.md 8(d) perf fixture): uniform random fields, scales ~ U(1e-3, 1.1e-2)."""
     G = math.ceil(K / groupsize)
+    half = 1 << (bits - 1)
     if bits == 3:
-        from . import ops as _ops
-        qw = _ops.pack_qweight(torch.randint(0, 8, (K, N), device=device, generator=gen, dtype=torch.int32), 3)
-        qz = _ops.pack_qzeros(torch.randint(0, 8, (G, N), device=device, generator=gen, dtype=torch.int32), 3)
+        qw = ops.pack_qweight(torch.randint(0, 8, (K, N), device=device, generator=gen, dtype=torch.int32), 3)
     else:
         qw = torch.randint(-2**31, 2**31 - 1, (K // 32 * bits, N), device=device, generator=gen, dtype=torch.int32)
-        qz = torch.randint(-2**31, 2**31 - 1, (G, N // 32 * bits), device=device, generator=gen, dtype=torch.int32)
+    # zero points centred on the weight grid like a real asymmetric GPTQ checkpoint (stored minus one: z = stored + 1 has the mean
+    # of the uniform fields, 2^(bits-1) - 1/2).  Fully random zeros give every weight the same mean offset, and a 32-layer stack of
+    # such matrices amplifies the common mode of the activations until fp16 overflows.
+    lo, hi = (half - 3, half + 1) if bits >= 4 else (half - 2, half)
+    qz = ops.pack_qzeros(torch.randint(lo, hi, (G, N), device=device, generator=gen, dtype=torch.int32), bits)
     s = (torch.rand(G, N, device=device, generator=gen) * 1e-2 + 1e-3).half()
     g = (torch.arange(K, device=device) // groupsize).to(torch.int32)
     if act_order:

@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+D=gptq-for-llama_b200/dev
+(timeout 120 python tools/dev_mega.py 4 > gpurun_out/dev_tiny.log 2>&1; echo "rc=$?" >> gpurun_out/dev_tiny.log)
+(GPTQ_B200_LIB=$D/libgptq_b200_exact.so timeout 120 python tools/dev_mega.py 4 > gpurun_out/dev_tiny_exact.log 2>&1; echo "rc=$?" >> gpurun_out/dev_tiny_exact.log)
+(timeout 120 python tools/dev_mega.py 3 act > gpurun_out/dev_tiny_3act.log 2>&1; echo "rc=$?" >> gpurun_out/dev_tiny_3act.log)
+(timeout 200 python tools/quick_bench.py 7b > gpurun_out/qb_7b.log 2>&1; echo "rc=$?" >> gpurun_out/qb_7b.log)
+(GPTQ_B200_LIB=$D/libgptq_b200_exact.so timeout 200 python tools/quick_bench.py 7b > gpurun_out/qb_7b_exact.log 2>&1; echo "rc=$?" >> gpurun_out/qb_7b_exact.log)
+(GPTQ_B200_LIB=$D/libgptq_b200_trace.so timeout 200 python tools/trace_mega.py 7b > gpurun_out/trace_7b.log 2>&1; echo "rc=$?" >> gpurun_out/trace_7b.log)
+(timeout 600 python -m pytest tests/test_gpu_engine.py -x -q > gpurun_out/t_engine.log 2>&1; echo "rc=$?" >> gpurun_out/t_engine.log)
+(timeout 1200 python -m pytest tests/test_gpu_engine_fullsize.py -q > gpurun_out/t_full.log 2>&1; echo "rc=$?" >> gpurun_out/t_full.log)
+tail -n 12 gpurun_out/dev_tiny.log gpurun_out/qb_7b.log gpurun_out/qb_7b_exact.log gpurun_out/t_engine.log gpurun_out/t_full.log

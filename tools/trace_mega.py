@@ -1,5 +1,6 @@
 """Device timeline of the persistent decode kernel (build with `make -C gptq-for-llama_b200/csrc variants`; run with
-GPTQ_B200_LIB=gptq-for-llama_b200/dev/libgptq_b200_trace.so).  %globaltimer per CTA at the phase boundaries of the first layers."""
+GPTQ_B200_LIB=gptq-for-llama_b200/dev/libgptq_b200_trace.so).  %globaltimer per CTA at the phase boundaries of the first layers,
+plus per-operation consumer counters of layer 2 (cycles in the op, cycles waiting for ring stages, stages)."""
 import ctypes, os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'gptq-for-llama_b200'))
@@ -16,6 +17,7 @@ assert raw.gptq_debug_set_mega_trace(buf.data_ptr()) == 0
 for _ in range(3):
     dec.step()
 torch.cuda.synchronize()
+print('logits finite:', bool(torch.isfinite(dec.logits).all()), 'rms', dec.logits.float().pow(2).mean().sqrt().item())
 t = buf.cpu().view(NCTA, 64).double()
 t0 = t[:, 0].min()
 names = ['Q start', 'Q x staged', 'Q matvec done', 'Q barrier passed', 'A done', 'A barrier passed', 'O done', 'O barrier passed', 'G x staged', 'G done', 'D start(after barrier)', 'D done']
@@ -25,3 +27,9 @@ for l in range(1, 4):
         c = (t[:, l * 12 + k] - t0) / 1e3
         print(f'  {names[k]:24s} {c.min().item():8.2f} {c.median().item():8.2f} {c.max().item():8.2f}')
     print(f'  layer total {((t[:, (l + 1) * 12] - t[:, l * 12]) / 1e3).median().item():.2f} us')
+print('layer 2, team 0 of every CTA (median over CTAs): cycles in op / waiting for stages / stages / busy cycles per stage')
+for i, name in enumerate(['Q', 'A', 'O', 'G', 'D']):
+    tot, wait, st = t[:, 48 + 3 * i], t[:, 49 + 3 * i], t[:, 50 + 3 * i]
+    busy = ((tot - wait) / st.clamp(min=1)).median().item()
+    print(f'  {name}: {tot.median().item():8.0f} {wait.median().item():8.0f} ({(wait / tot.clamp(min=1)).median().item():.0%}) {st.median().item():5.0f}   {busy:7.0f}')
+print(f'producer (team 0) cycles blocked on a full ring over the whole token: median {t[:, 63].median().item():.0f} ({t[:, 63].median().item() / 1.965e3:.0f} us)')
