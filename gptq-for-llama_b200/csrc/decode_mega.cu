@@ -77,7 +77,7 @@ namespace {
 
 #define MTRACE(id)                                                                                                       \
     do {                                                                                                                 \
-        if (g_mega_trace != nullptr && threadIdx.x == 0 && (id) < 48) {                                                   \
+        if (g_mega_trace != nullptr && threadIdx.x == 0 && (id) < 36) {                                                   \
             unsigned long long t_;                                                                                       \
             asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_));                                                        \
             g_mega_trace[blockIdx.x * 64 + (id)] = t_;                                                                   \
@@ -520,8 +520,7 @@ __device__ __forceinline__ void mma_16816_z(float (&d)[4], uint32_t a0, uint32_t
 
 // the four A registers (k-pairs (0,4), (1,5), (2,6), (3,7)) of one packed word
 __device__ __forceinline__ void nibble_regs(uint32_t q, uint32_t (&a)[4]) {
-    uint32_t q8;  // q >> 8 as a multiply-high: IMAD.HI runs on the FMA pipe, the masks below saturate the integer ALU pipe
-    asm("mul.hi.u32 %0, %1, 0x01000000;" : "=r"(q8) : "r"(q));
+    const uint32_t q8 = q >> 8;  // (as IMAD.HI on the FMA pipe it is far slower: tools/ubench/loop.cu, 1102 vs 817 cycles per stage)
     if (kSubnormal) {  // masked in place: fp16 subnormals n * 2^-24 and 16 n * 2^-24
         a[0] = q & 0x000f000fu;
         a[1] = q & 0x00f000f0u;
@@ -639,6 +638,9 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
             xsum = xsum_full + ks0;
         } else {
             // stage this segment's k-range [ks0*32, (ks0+nseg)*32) of the op input into the team's buffer
+#ifdef GPTQ_TRACE
+            const long long stg0 = clock64();
+#endif
             team_sync(tc.team);  // previous readers of xseg are done
             const int kbeg = ks0 * 32;
             if constexpr (XMODE == X_SWIGLU) {  // h = fp16(silu(acc_gate) * acc_up)  (quant/fused_mlp.py:163-165)
@@ -654,47 +656,115 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
                 }
             } else {
                 // attention output: softmax-merge of the partial records (m, l, o[128]) the teams wrote for the head; which records
-                // belong to a head is in the CTA's merge table (build_merge_table, once per launch).  All loads are independent.
-                for (int e = tc.ttid; e < nseg * 32; e += kTeamThreads) {
-                    int k = kbeg + e;
-                    if constexpr (ACT) {
-                        if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
+                // belong to a head is in the CTA's merge table (build_merge_table, once per launch).
+                constexpr int kBatch = 12;  // records fetched per round trip (a 7B head has at most 12)
+                int h_lo = kbeg / kHD, h_hi = (kbeg + nseg * 32 - 1) / kHD;
+                bool fast = (h_hi - h_lo) < kTeamWarps;
+                if constexpr (ACT) fast = fast && (perm == nullptr);
+                if (fast)
+                    for (int hd = h_lo; hd <= h_hi; ++hd) {
+                        const unsigned rg = tc.mt_range[hd];
+                        fast = fast && ((int)(rg >> 16) - (int)(rg & 0xffffu) <= kBatch);
                     }
-                    const int head = k / kHD, d = k - head * kHD;
-                    const unsigned range = tc.mt_range[head];
-                    const int e0 = (int)(range & 0xffffu), e1 = (int)(range >> 16);
-                    float M = -INFINITY, Ls = 0.f, O = 0.f;
-                    constexpr int kBatch = 12;  // records fetched per round trip (a 7B head has at most 12)
-#pragma unroll 1
-                    for (int eb = e0; eb < e1; eb += kBatch) {
-                        float mv[kBatch], lv[kBatch], ov[kBatch];
-#pragma unroll
-                        for (int i = 0; i < kBatch; ++i) {  // all loads of the batch are in flight together
-                            const unsigned ri = (eb + i < e1) ? (unsigned)tc.mt_rec[eb + i] : 0xffffu;
-                            const float* rc = p.part + (size_t)(ri == 0xffffu ? 0u : ri) * kRec;
-                            const float m = ld_cg(rc), l = ld_cg(rc + 1), o = ld_cg(rc + 4 + d);
-                            mv[i] = ri == 0xffffu ? -INFINITY : m;
-                            lv[i] = ri == 0xffffu ? 0.f : l;
-                            ov[i] = ri == 0xffffu ? 0.f : o;
-                        }
-                        float Mb = M;
-#pragma unroll
-                        for (int i = 0; i < kBatch; ++i) Mb = fmaxf(Mb, mv[i]);
-                        const float w0 = (M == -INFINITY) ? 0.f : expf(M - Mb);
-                        Ls *= w0;
-                        O *= w0;
+                float* wts = reinterpret_cast<float*>(tc.scratch);  // [kTeamWarps][kBatch] merge weights of the segment's heads
+                if (fast) {
+                    // ONE round trip (per 256 features): every thread fetches the o values of its feature from all records of its
+                    // head while warp w fetches (m, l) of head h_lo + w and turns them into merge weights exp(m - M) / L.
+                    const int nfeat = nseg * 32;
+                    float ov[kBatch];
+                    int head = h_lo;
+                    auto fetch = [&](int e) {
+                        const bool active = e < nfeat;
+                        const int k = kbeg + (active ? e : 0);
+                        head = k / kHD;
+                        const int d = k - head * kHD;
+                        const unsigned range = tc.mt_range[head];
+                        const int e0 = (int)(range & 0xffffu), e1 = (int)(range >> 16);
 #pragma unroll
                         for (int i = 0; i < kBatch; ++i) {
-                            const float w = (mv[i] == -INFINITY) ? 0.f : expf(mv[i] - Mb);
-                            Ls = fmaf(lv[i], w, Ls);
-                            O = fmaf(ov[i], w, O);
+                            const unsigned ri = (active && e0 + i < e1) ? (unsigned)tc.mt_rec[e0 + i] : 0xffffu;
+                            ov[i] = (ri == 0xffffu) ? 0.f : ld_cg(p.part + (size_t)ri * kRec + 4 + d);
                         }
-                        M = Mb;
+                    };
+                    auto emit = [&](int e) {
+                        if (e < nfeat) {
+                            float O = 0.f;
+#pragma unroll
+                            for (int i = 0; i < kBatch; ++i) O = fmaf(wts[(head - h_lo) * kBatch + i], ov[i], O);
+                            __half hv = __float2half_rn(O);
+                            const int j8 = e & 7;
+                            if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
+                            tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
+                        }
+                    };
+                    fetch(tc.ttid);
+                    if (h_lo + tc.wt <= h_hi) {
+                        const unsigned rg = tc.mt_range[h_lo + tc.wt];
+                        const int f0 = (int)(rg & 0xffffu), f1 = (int)(rg >> 16);
+                        const unsigned ri = (lane < kBatch && f0 + lane < f1) ? (unsigned)tc.mt_rec[f0 + lane] : 0xffffu;
+                        float m = -INFINITY, l = 0.f;
+                        if (ri != 0xffffu) {
+                            m = ld_cg(p.part + (size_t)ri * kRec);
+                            l = ld_cg(p.part + (size_t)ri * kRec + 1);
+                        }
+                        float M = m;
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));  // lanes 0..15 hold the batch
+                        M = __shfl_sync(0xffffffffu, M, 0);
+                        const float w = (m == -INFINITY) ? 0.f : expf(m - M);
+                        float L = l * w;
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+                        L = __shfl_sync(0xffffffffu, L, 0);
+                        if (lane < kBatch) wts[tc.wt * kBatch + lane] = w / L;
                     }
-                    __half hv = __float2half_rn(O / Ls);
-                    const int j8 = e & 7;
-                    if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
-                    tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
+                    team_sync(tc.team);
+                    emit(tc.ttid);
+                    for (int e = tc.ttid + kTeamThreads; e - tc.ttid < nfeat; e += kTeamThreads) {  // wider segments (13B, 65B): further round trips
+                        fetch(e);
+                        emit(e);
+                    }
+                } else {
+                    for (int e = tc.ttid; e < nseg * 32; e += kTeamThreads) {
+                        int k = kbeg + e;
+                        if constexpr (ACT) {
+                            if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
+                        }
+                        const int head = k / kHD, d = k - head * kHD;
+                        const unsigned range = tc.mt_range[head];
+                        const int e0 = (int)(range & 0xffffu), e1 = (int)(range >> 16);
+                        float M = -INFINITY, Ls = 0.f, O = 0.f;
+#pragma unroll 1
+                        for (int eb = e0; eb < e1; eb += kBatch) {
+                            float mv[kBatch], lv[kBatch], ov[kBatch];
+#pragma unroll
+                            for (int i = 0; i < kBatch; ++i) {  // all loads of the batch are in flight together
+                                const unsigned ri = (eb + i < e1) ? (unsigned)tc.mt_rec[eb + i] : 0xffffu;
+                                const float* rc = p.part + (size_t)(ri == 0xffffu ? 0u : ri) * kRec;
+                                const float m = ld_cg(rc), l = ld_cg(rc + 1), o = ld_cg(rc + 4 + d);
+                                mv[i] = ri == 0xffffu ? -INFINITY : m;
+                                lv[i] = ri == 0xffffu ? 0.f : l;
+                                ov[i] = ri == 0xffffu ? 0.f : o;
+                            }
+                            float Mb = M;
+#pragma unroll
+                            for (int i = 0; i < kBatch; ++i) Mb = fmaxf(Mb, mv[i]);
+                            const float w0 = (M == -INFINITY) ? 0.f : expf(M - Mb);
+                            Ls *= w0;
+                            O *= w0;
+#pragma unroll
+                            for (int i = 0; i < kBatch; ++i) {
+                                const float w = (mv[i] == -INFINITY) ? 0.f : expf(mv[i] - Mb);
+                                Ls = fmaf(lv[i], w, Ls);
+                                O = fmaf(ov[i], w, O);
+                            }
+                            M = Mb;
+                        }
+                        __half hv = __float2half_rn(O / Ls);
+                        const int j8 = e & 7;
+                        if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
+                        tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
+                    }
                 }
             }
             team_sync(tc.team);
@@ -702,6 +772,9 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
             team_sync(tc.team);
             xaddr = smem_u32(tc.xseg) + (t * 8) * 2;
             xsum = tc.xsum_seg;
+#ifdef GPTQ_TRACE
+            if (g_mega_trace != nullptr && threadIdx.x == 0) g_mega_trace[blockIdx.x * 64 + 36 + XMODE] += (unsigned long long)(clock64() - stg0);
+#endif
         }
 
         float tot = 0.f;  // lane (g, t) finishes column 4g + t of the warp's stripe

@@ -21,7 +21,7 @@ print('logits finite:', bool(torch.isfinite(dec.logits).all()), 'rms', dec.logit
 t = buf.cpu().view(NCTA, 64).double()
 t0 = t[:, 0].min()
 names = ['Q start', 'Q x staged', 'Q matvec done', 'Q barrier passed', 'A done', 'A barrier passed', 'O done', 'O barrier passed', 'G x staged', 'G done', 'D start(after barrier)', 'D done']
-for l in range(1, 4):
+for l in range(1, 3):
     print(f'layer {l}: (min / median / max over CTAs, us since kernel start)')
     for k in range(12):
         c = (t[:, l * 12 + k] - t0) / 1e3
@@ -32,4 +32,5 @@ for i, name in enumerate(['Q', 'A', 'O', 'G', 'D']):
     tot, wait, st = t[:, 48 + 3 * i], t[:, 49 + 3 * i], t[:, 50 + 3 * i]
     busy = ((tot - wait) / st.clamp(min=1)).median().item()
     print(f'  {name}: {tot.median().item():8.0f} {wait.median().item():8.0f} ({(wait / tot.clamp(min=1)).median().item():.0%}) {st.median().item():5.0f}   {busy:7.0f}')
+print(f'staging cycles inside the ops, summed over all layers / 32 (team 0): O (attention merge) {t[:, 37].median().item() / 32 / 3:.0f}, D (SwiGLU) {t[:, 38].median().item() / 32 / 3:.0f}')
 print(f'producer (team 0) cycles blocked on a full ring over the whole token: median {t[:, 63].median().item():.0f} ({t[:, 63].median().item() / 1.965e3:.0f} us)')
