@@ -147,7 +147,7 @@ struct MegaParams {
     float* acc_g;      // [I]
     float* acc_u;      // [I]
     float* acc_d;      // [H]
-    float* part;       // [teams][2][kRec]  attention partial records
+    float* part;       // [teams][kRec]  attention partial records (m, l, pad, pad, o[128]), one per team and layer
     float* rope_cs;    // [128]: cos[64], sin[64] of this step's position
     unsigned long long* bar;  // [0]: monotonic arrival counter of the grid barrier, [1]: its value when the previous launch ended
     LayerDesc layers[kMaxLayers];
@@ -160,6 +160,36 @@ __device__ __forceinline__ void team_range(unsigned T, unsigned U, unsigned nb, 
     a = (int)((T * U) / nb);  // T * U < 2^32 (checked by mega_plan)
     b = (int)(((T + 1) * U) / nb);
 }
+// Attention: the teams are dealt to the heads (nb / n_heads or one more each), a head's 32-key units to its teams: no team meets two
+// heads, so every team writes exactly one partial record per layer (a neutral one if it has no unit).
+struct HeadTeams {
+    int first, count;  // teams [first, first + count) serve the head
+};
+__device__ __forceinline__ HeadTeams head_teams(int head, int n_heads, unsigned nb) {
+    const int base = (int)nb / n_heads, rem = (int)nb % n_heads;
+    HeadTeams h;
+    h.first = head * base + min(head, rem);
+    h.count = base + (head < rem ? 1 : 0);
+    return h;
+}
+// (head, unit range [b0, b1) inside the head) of team T for a context of upb units per head
+__device__ __forceinline__ void attn_range(unsigned T, int n_heads, unsigned nb, int upb, int& head, int& b0, int& b1) {
+    const int base = (int)nb / n_heads, rem = (int)nb % n_heads;
+    const int split = rem * (base + 1);
+    int idx, cnt;
+    if ((int)T < split) {
+        head = (int)T / (base + 1);
+        idx = (int)T - head * (base + 1);
+        cnt = base + 1;
+    } else {
+        head = rem + ((int)T - split) / base;
+        idx = ((int)T - split) % base;
+        cnt = base;
+    }
+    b0 = idx * upb / cnt;
+    b1 = (idx + 1) * upb / cnt;
+}
+
 // k-steps of the stage that starts `gpos` steps into its quantisation group, in a segment with `left` steps to go
 __device__ __forceinline__ int stage_steps(int gpos, int gs_steps, int left) { return min(min(kStageSteps, gs_steps - gpos), left); }
 
@@ -248,13 +278,12 @@ __device__ void produce_matvec(ProdRing& r, const MegaParams& p, const MatDesc* 
 __device__ void produce_kv(ProdRing& r, const MegaParams& p, int layer, unsigned T, unsigned nb) {
     const int Tlen = step_pos(p) + 1;
     const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
-    int u, u1;
-    team_range(T, (unsigned)(p.n_heads * upb), nb, u, u1);
+    int head, b, b1;
+    attn_range(T, p.n_heads, nb, upb, head, b, b1);
     const __half* kc = p.k_cache + layer * p.layer_stride;
     const __half* vc = p.v_cache + layer * p.layer_stride;
 #pragma unroll 1
-    for (; u < u1; ++u) {
-        const int head = u / upb, b = u - head * upb;
+    for (; b < b1; ++b) {
         const int nrows = min(kKeysPerUnit, Tlen - b * kKeysPerUnit);
         const size_t off = ((size_t)head * p.max_seq + (size_t)b * kKeysPerUnit) * kHD;
         uint32_t bar;
@@ -562,42 +591,141 @@ struct TeamCtx {
     __half* xseg;              // this team's half of the xs buffer (per-segment inputs of O and D)
     float* xsum_seg;
     uint8_t* scratch;          // kTeamScratch bytes
-    const unsigned short* mt_rec;  // merge table (per CTA): entry e = team + head -> attention record index (0xffff: none)
-    const unsigned* mt_range;      // [n_heads]: entry range e0 | e1 << 16 of the head
 };
 
-// Which attention partial records belong to which head: a function of the step's position only, computed once per launch by
-// every CTA into its shared memory.  Entry index e = Tt + head is unique (consecutive heads share at most one team).
-__device__ void build_merge_table(const MegaParams& p, unsigned nb, unsigned short* mt_rec, unsigned* mt_range) {
-    const int tid = threadIdx.x;
-    const int Tlen = step_pos(p) + 1;
-    const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
-    const unsigned Ua = (unsigned)(p.n_heads * upb);
-    const int n_ent = (int)nb + p.n_heads;
-    for (int e = tid; e < n_ent; e += kConsumers) mt_rec[e] = 0xffffu;
-    cta_sync();
-    for (unsigned Tt = tid; Tt < nb; Tt += kConsumers) {
-        int a, b;
-        team_range(Tt, Ua, nb, a, b);
-        if (a < b) {
-            const int hf = a / upb, hl = (b - 1) / upb;  // first / last head of the team (at most two heads)
-            mt_rec[Tt + hf] = (unsigned short)(Tt * 2);
-            if (hl != hf) mt_rec[Tt + hl] = (unsigned short)(Tt * 2 + 1);
+
+// Input of o_proj (XMODE == X_ATTN) / down_proj (X_SWIGLU) for the team's WHOLE unit range [u0, u1) (units = k-steps of 32, numbered
+// slab-major; the range wraps at most once from the end of one slab's k-range to the start of the next): staged once, in unit order,
+// into the team's half of the xs buffer with its per-step sums.  One L2 round trip for the common shapes.
+template <int XMODE, bool ACT>
+__device__ void stage_range(const MegaParams& p, const TeamCtx& tc, int nk, int u0, int u1, const int32_t* perm) {
+    const int lane = tc.lane;
+    const int nun = u1 - u0, nfeat = nun * 32;
+    const int ksb = u0 % nk;  // k-step of the first unit
+    auto k_of = [&](int e) {  // feature e of the range -> input index k
+        int ks = ksb + (e >> 5);
+        if (ks >= nk) ks -= nk;
+        return ks * 32 + (e & 31);
+    };
+    team_sync(tc.team);  // previous readers of xseg are done
+    if constexpr (XMODE == X_SWIGLU) {  // h = fp16(silu(acc_gate) * acc_up)  (quant/fused_mlp.py:163-165)
+        for (int c = tc.ttid; c < nun * 4; c += kTeamThreads) {
+            const int k = k_of(c * 8);
+            const float4 g0 = ld_cg4(p.acc_g + k), g1 = ld_cg4(p.acc_g + k + 4);
+            const float4 a0 = ld_cg4(p.acc_u + k), a1 = ld_cg4(p.acc_u + k + 4);
+            const uint32_t o0 = h2_as_u32(__floats2half2_rn(swiglu(g0.x, a0.x), swiglu(g0.y, a0.y)));
+            const uint32_t o1 = h2_as_u32(__floats2half2_rn(swiglu(g0.z, a0.z), swiglu(g0.w, a0.w)));
+            const uint32_t o2 = h2_as_u32(__floats2half2_rn(swiglu(g1.x, a1.x), swiglu(g1.y, a1.y)));
+            const uint32_t o3 = h2_as_u32(__floats2half2_rn(swiglu(g1.z, a1.z), swiglu(g1.w, a1.w)));
+            *reinterpret_cast<uint4*>(tc.xseg + c * 8) = perm8(o0, o1, o2, o3);
+        }
+    } else {
+        // attention output: softmax-merge of the partial records (m, l, o[128]) of the head's teams (head_teams: contiguous, one
+        // record each).
+        constexpr int kBatch = 12;  // records fetched per round trip (a 7B head has 9 or 10 teams)
+        auto put = [&](int e, float v) {
+            __half hv = __float2half_rn(v);
+            const int j8 = e & 7;
+            if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
+            tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
+        };
+        // heads of the range: [hA0, hA1] before the wrap, [0, hB1] after it
+        const int nA = min(nun, nk - ksb);
+        const int hA0 = (ksb * 32) / kHD, hA1 = ((ksb + nA) * 32 - 1) / kHD;
+        const int nslotA = hA1 - hA0 + 1, nslotB = (nun > nA) ? ((nun - nA) * 32 - 1) / kHD + 1 : 0;
+        bool fast = (nslotA + nslotB <= kTeamWarps) && (nun <= nk) && ((int)tc.nb / p.n_heads + 1 <= kBatch);
+        if constexpr (ACT) fast = fast && (perm == nullptr);
+        if (fast) {
+            // ONE round trip (per 256 features): every thread fetches the o values of its feature from all records of its head while
+            // warp w fetches (m, l) of the w-th head of the range and turns them into merge weights exp(m - M) / L.
+            float* wts = reinterpret_cast<float*>(tc.scratch);  // [kTeamWarps][kBatch]
+            float ov[kBatch];
+            int slot = 0;
+            auto fetch = [&](int e) {
+                const bool active = e < nfeat;
+                const int k = k_of(active ? e : 0);
+                const int head = k / kHD, d = k - head * kHD;
+                slot = ((e >> 5) < nA) ? head - hA0 : nslotA + head;
+                const HeadTeams ht = head_teams(head, p.n_heads, tc.nb);
+#pragma unroll
+                for (int i = 0; i < kBatch; ++i) ov[i] = (active && i < ht.count) ? ld_cg(p.part + (size_t)(ht.first + i) * kRec + 4 + d) : 0.f;
+            };
+            auto emit = [&](int e) {
+                if (e < nfeat) {
+                    float O = 0.f;
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) O = fmaf(wts[slot * kBatch + i], ov[i], O);
+                    put(e, O);
+                }
+            };
+            fetch(tc.ttid);
+            if (tc.wt < nslotA + nslotB) {
+                const int head = tc.wt < nslotA ? hA0 + tc.wt : tc.wt - nslotA;
+                const HeadTeams ht = head_teams(head, p.n_heads, tc.nb);
+                float m = -INFINITY, l = 0.f;
+                if (lane < ht.count) {
+                    m = ld_cg(p.part + (size_t)(ht.first + lane) * kRec);
+                    l = ld_cg(p.part + (size_t)(ht.first + lane) * kRec + 1);
+                }
+                float M = m;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));  // lanes 0..15 hold the batch
+                M = __shfl_sync(0xffffffffu, M, 0);
+                const float w = (m == -INFINITY) ? 0.f : expf(m - M);
+                float L = l * w;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
+                L = __shfl_sync(0xffffffffu, L, 0);
+                if (lane < kBatch) wts[tc.wt * kBatch + lane] = w / L;
+            }
+            team_sync(tc.team);
+            emit(tc.ttid);
+            for (int e = tc.ttid + kTeamThreads; e - tc.ttid < nfeat; e += kTeamThreads) {  // wider ranges (13B, 65B): further round trips
+                fetch(e);
+                emit(e);
+            }
+        } else {
+            for (int e = tc.ttid; e < nfeat; e += kTeamThreads) {
+                int k = k_of(e);
+                if constexpr (ACT) {
+                    if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
+                }
+                const int head = k / kHD, d = k - head * kHD;
+                const HeadTeams ht = head_teams(head, p.n_heads, tc.nb);
+                float M = -INFINITY, Ls = 0.f, O = 0.f;
+#pragma unroll 1
+                for (int ib = 0; ib < ht.count; ib += kBatch) {
+                    float mv[kBatch], lv[kBatch], ov[kBatch];
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) {  // all loads of the batch are in flight together
+                        const bool on = ib + i < ht.count;
+                        const float* rc = p.part + (size_t)(ht.first + (on ? ib + i : 0)) * kRec;
+                        const float m = ld_cg(rc), l = ld_cg(rc + 1), o = ld_cg(rc + 4 + d);
+                        mv[i] = on ? m : -INFINITY;
+                        lv[i] = on ? l : 0.f;
+                        ov[i] = on ? o : 0.f;
+                    }
+                    float Mb = M;
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) Mb = fmaxf(Mb, mv[i]);
+                    const float w0 = (M == -INFINITY) ? 0.f : expf(M - Mb);
+                    Ls *= w0;
+                    O *= w0;
+#pragma unroll
+                    for (int i = 0; i < kBatch; ++i) {
+                        const float w = (mv[i] == -INFINITY) ? 0.f : expf(mv[i] - Mb);
+                        Ls = fmaf(lv[i], w, Ls);
+                        O = fmaf(ov[i], w, O);
+                    }
+                    M = Mb;
+                }
+                put(e, O / Ls);
+            }
         }
     }
-    for (int hd = tid; hd < p.n_heads; hd += kConsumers) {
-        // teams that can hold units of the head: from the one whose range reaches unit hd * upb to the one holding its last unit
-        const unsigned t0 = ((unsigned)(hd * upb) * nb) / Ua;
-        unsigned t1 = ((unsigned)((hd + 1) * upb - 1) * nb) / Ua;
-        int a, b;
-        team_range(t1, Ua, nb, a, b);
-        while (b <= (hd + 1) * upb - 1 && t1 + 1 < nb) {  // floor(u * nb / U) can fall one team short of the owner of unit u
-            ++t1;
-            team_range(t1, Ua, nb, a, b);
-        }
-        mt_range[hd] = (t0 + hd) | ((t1 + hd + 1) << 16);
-    }
-    cta_sync();
+    team_sync(tc.team);
+    compute_xsum(tc.xseg, nun, tc.xsum_seg, tc.ttid, kTeamThreads);
+    team_sync(tc.team);
 }
 
 // One matvec op for this team: consume the stages of its unit range from the ring, RED the results.
@@ -622,6 +750,18 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
     const uint32_t lane_z = (uint32_t)(kZeroOff + (tc.wt * 4 + (cg >> 1)) * 4);    // the qzeros word holding its zero
     const int zshift = (cg & 1) * 16 + t * 4;
     const float unit = kSubnormal ? 16777216.0f : 1.0f;  // the accumulators are in units of 2^-24
+    const int u_begin = u;
+    if constexpr (XMODE != X_FULL) {
+        if (u < u_end) {
+#ifdef GPTQ_TRACE
+            const long long stg0 = clock64();
+#endif
+            stage_range<XMODE, ACT>(p, tc, nk, u, u_end, perm);
+#ifdef GPTQ_TRACE
+            if (g_mega_trace != nullptr && threadIdx.x == 0) g_mega_trace[blockIdx.x * 64 + 36 + XMODE] += (unsigned long long)(clock64() - stg0);
+#endif
+        }
+    }
 
 #pragma unroll 1
     while (u < u_end) {
@@ -637,144 +777,8 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
             xaddr = smem_u32(xs_full) + (ks0 * 32 + t * 8) * 2;
             xsum = xsum_full + ks0;
         } else {
-            // stage this segment's k-range [ks0*32, (ks0+nseg)*32) of the op input into the team's buffer
-#ifdef GPTQ_TRACE
-            const long long stg0 = clock64();
-#endif
-            team_sync(tc.team);  // previous readers of xseg are done
-            const int kbeg = ks0 * 32;
-            if constexpr (XMODE == X_SWIGLU) {  // h = fp16(silu(acc_gate) * acc_up)  (quant/fused_mlp.py:163-165)
-                for (int c = tc.ttid; c < nseg * 4; c += kTeamThreads) {
-                    const int k = kbeg + c * 8;
-                    const float4 g0 = ld_cg4(p.acc_g + k), g1 = ld_cg4(p.acc_g + k + 4);
-                    const float4 u0 = ld_cg4(p.acc_u + k), u1 = ld_cg4(p.acc_u + k + 4);
-                    const uint32_t o0 = h2_as_u32(__floats2half2_rn(swiglu(g0.x, u0.x), swiglu(g0.y, u0.y)));
-                    const uint32_t o1 = h2_as_u32(__floats2half2_rn(swiglu(g0.z, u0.z), swiglu(g0.w, u0.w)));
-                    const uint32_t o2 = h2_as_u32(__floats2half2_rn(swiglu(g1.x, u1.x), swiglu(g1.y, u1.y)));
-                    const uint32_t o3 = h2_as_u32(__floats2half2_rn(swiglu(g1.z, u1.z), swiglu(g1.w, u1.w)));
-                    *reinterpret_cast<uint4*>(tc.xseg + c * 8) = perm8(o0, o1, o2, o3);
-                }
-            } else {
-                // attention output: softmax-merge of the partial records (m, l, o[128]) the teams wrote for the head; which records
-                // belong to a head is in the CTA's merge table (build_merge_table, once per launch).
-                constexpr int kBatch = 12;  // records fetched per round trip (a 7B head has at most 12)
-                int h_lo = kbeg / kHD, h_hi = (kbeg + nseg * 32 - 1) / kHD;
-                bool fast = (h_hi - h_lo) < kTeamWarps;
-                if constexpr (ACT) fast = fast && (perm == nullptr);
-                if (fast)
-                    for (int hd = h_lo; hd <= h_hi; ++hd) {
-                        const unsigned rg = tc.mt_range[hd];
-                        fast = fast && ((int)(rg >> 16) - (int)(rg & 0xffffu) <= kBatch);
-                    }
-                float* wts = reinterpret_cast<float*>(tc.scratch);  // [kTeamWarps][kBatch] merge weights of the segment's heads
-                if (fast) {
-                    // ONE round trip (per 256 features): every thread fetches the o values of its feature from all records of its
-                    // head while warp w fetches (m, l) of head h_lo + w and turns them into merge weights exp(m - M) / L.
-                    const int nfeat = nseg * 32;
-                    float ov[kBatch];
-                    int head = h_lo;
-                    auto fetch = [&](int e) {
-                        const bool active = e < nfeat;
-                        const int k = kbeg + (active ? e : 0);
-                        head = k / kHD;
-                        const int d = k - head * kHD;
-                        const unsigned range = tc.mt_range[head];
-                        const int e0 = (int)(range & 0xffffu), e1 = (int)(range >> 16);
-#pragma unroll
-                        for (int i = 0; i < kBatch; ++i) {
-                            const unsigned ri = (active && e0 + i < e1) ? (unsigned)tc.mt_rec[e0 + i] : 0xffffu;
-                            ov[i] = (ri == 0xffffu) ? 0.f : ld_cg(p.part + (size_t)ri * kRec + 4 + d);
-                        }
-                    };
-                    auto emit = [&](int e) {
-                        if (e < nfeat) {
-                            float O = 0.f;
-#pragma unroll
-                            for (int i = 0; i < kBatch; ++i) O = fmaf(wts[(head - h_lo) * kBatch + i], ov[i], O);
-                            __half hv = __float2half_rn(O);
-                            const int j8 = e & 7;
-                            if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
-                            tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
-                        }
-                    };
-                    fetch(tc.ttid);
-                    if (h_lo + tc.wt <= h_hi) {
-                        const unsigned rg = tc.mt_range[h_lo + tc.wt];
-                        const int f0 = (int)(rg & 0xffffu), f1 = (int)(rg >> 16);
-                        const unsigned ri = (lane < kBatch && f0 + lane < f1) ? (unsigned)tc.mt_rec[f0 + lane] : 0xffffu;
-                        float m = -INFINITY, l = 0.f;
-                        if (ri != 0xffffu) {
-                            m = ld_cg(p.part + (size_t)ri * kRec);
-                            l = ld_cg(p.part + (size_t)ri * kRec + 1);
-                        }
-                        float M = m;
-#pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));  // lanes 0..15 hold the batch
-                        M = __shfl_sync(0xffffffffu, M, 0);
-                        const float w = (m == -INFINITY) ? 0.f : expf(m - M);
-                        float L = l * w;
-#pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) L += __shfl_xor_sync(0xffffffffu, L, o);
-                        L = __shfl_sync(0xffffffffu, L, 0);
-                        if (lane < kBatch) wts[tc.wt * kBatch + lane] = w / L;
-                    }
-                    team_sync(tc.team);
-                    emit(tc.ttid);
-                    for (int e = tc.ttid + kTeamThreads; e - tc.ttid < nfeat; e += kTeamThreads) {  // wider segments (13B, 65B): further round trips
-                        fetch(e);
-                        emit(e);
-                    }
-                } else {
-                    for (int e = tc.ttid; e < nseg * 32; e += kTeamThreads) {
-                        int k = kbeg + e;
-                        if constexpr (ACT) {
-                            if (perm != nullptr) k = perm[k];  // regrouped rows: position k' of the matvec input is attention feature perm[k']
-                        }
-                        const int head = k / kHD, d = k - head * kHD;
-                        const unsigned range = tc.mt_range[head];
-                        const int e0 = (int)(range & 0xffffu), e1 = (int)(range >> 16);
-                        float M = -INFINITY, Ls = 0.f, O = 0.f;
-#pragma unroll 1
-                        for (int eb = e0; eb < e1; eb += kBatch) {
-                            float mv[kBatch], lv[kBatch], ov[kBatch];
-#pragma unroll
-                            for (int i = 0; i < kBatch; ++i) {  // all loads of the batch are in flight together
-                                const unsigned ri = (eb + i < e1) ? (unsigned)tc.mt_rec[eb + i] : 0xffffu;
-                                const float* rc = p.part + (size_t)(ri == 0xffffu ? 0u : ri) * kRec;
-                                const float m = ld_cg(rc), l = ld_cg(rc + 1), o = ld_cg(rc + 4 + d);
-                                mv[i] = ri == 0xffffu ? -INFINITY : m;
-                                lv[i] = ri == 0xffffu ? 0.f : l;
-                                ov[i] = ri == 0xffffu ? 0.f : o;
-                            }
-                            float Mb = M;
-#pragma unroll
-                            for (int i = 0; i < kBatch; ++i) Mb = fmaxf(Mb, mv[i]);
-                            const float w0 = (M == -INFINITY) ? 0.f : expf(M - Mb);
-                            Ls *= w0;
-                            O *= w0;
-#pragma unroll
-                            for (int i = 0; i < kBatch; ++i) {
-                                const float w = (mv[i] == -INFINITY) ? 0.f : expf(mv[i] - Mb);
-                                Ls = fmaf(lv[i], w, Ls);
-                                O = fmaf(ov[i], w, O);
-                            }
-                            M = Mb;
-                        }
-                        __half hv = __float2half_rn(O / Ls);
-                        const int j8 = e & 7;
-                        if (perm_scaled(j8)) hv = __hmul(hv, __float2half_rn(0.0625f));
-                        tc.xseg[(e & ~7) + perm_pos(j8)] = hv;
-                    }
-                }
-            }
-            team_sync(tc.team);
-            compute_xsum(tc.xseg, nseg, tc.xsum_seg, tc.ttid, kTeamThreads);
-            team_sync(tc.team);
-            xaddr = smem_u32(tc.xseg) + (t * 8) * 2;
-            xsum = tc.xsum_seg;
-#ifdef GPTQ_TRACE
-            if (g_mega_trace != nullptr && threadIdx.x == 0) g_mega_trace[blockIdx.x * 64 + 36 + XMODE] += (unsigned long long)(clock64() - stg0);
-#endif
+            xaddr = smem_u32(tc.xseg) + ((u - u_begin) * 32 + t * 8) * 2;
+            xsum = tc.xsum_seg + (u - u_begin);
         }
 
         float tot = 0.f;  // lane (g, t) finishes column 4g + t of the warp's stripe
@@ -832,13 +836,13 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
 }
 
 // ---- attention ----------------------------------------------------------------------------------------------------------
-// Work units (head, 32 keys), dealt to the teams as contiguous ranges (a team meets at most two heads); one unit = one
-// ring stage (K rows, V rows).  Per head-segment the team writes one partial record (m, l, o[128]) to p.part[T][rec].
+// Work units (head, 32 keys); a team serves one head (attn_range); one unit = one ring stage (K rows, V rows).  The team writes
+// one partial record (m, l, o[128]) to p.part[T].
 __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, int layer) {
     const int pos = step_pos(p), Tlen = pos + 1;
     const int upb = (Tlen + kKeysPerUnit - 1) / kKeysPerUnit;
-    int u, u_end;
-    team_range(tc.T, (unsigned)(p.n_heads * upb), tc.nb, u, u_end);
+    int head, b0, b_end;
+    attn_range(tc.T, p.n_heads, tc.nb, upb, head, b0, b_end);
     float* red_o = reinterpret_cast<float*>(tc.scratch);                 // [8][128]  end of a segment
     float* red_ml = reinterpret_cast<float*>(tc.scratch + 4096);         // [8][2]
     float* q_s = reinterpret_cast<float*>(tc.scratch);                   // [128]     start of a segment (aliases red_o)
@@ -848,13 +852,19 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
     const int ub_new = pos / kKeysPerUnit;  // the unit that holds this step's key
     __half* kc_l = p.k_cache + layer * p.layer_stride;
     __half* vc_l = p.v_cache + layer * p.layer_stride;
-    int rec = 0;
-#pragma unroll 1
-    while (u < u_end) {
-        const int head = u / upb, b0 = u - head * upb;
-        const int nseg = min(upb - b0, u_end - u);
-        const bool owns_new = (ub_new >= b0 && ub_new < b0 + nseg);
-        team_sync(tc.team);  // scratch reuse across segments
+    float* rec = p.part + (size_t)tc.T * kRec;
+    if (b0 >= b_end) {  // no unit for this team (short context): a neutral record keeps the merge uniform
+        if (ttid < kHD) rec[4 + ttid] = 0.f;
+        if (ttid == 0) {
+            rec[0] = -INFINITY;
+            rec[1] = 0.f;
+        }
+        return;
+    }
+    {
+        const int nseg = b_end - b0;
+        const bool owns_new = (ub_new >= b0 && ub_new < b_end);
+        team_sync(tc.team);  // scratch reuse
         if (ttid < kHD) {
             const int i = ttid & 63;
             const bool hi = ttid >= 64;
@@ -975,15 +985,12 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
                 L = fmaf(red_ml[w * 2 + 1], wgt, L);
                 O = fmaf(red_o[w * kHD + ttid], wgt, O);
             }
-            float* dst = p.part + ((size_t)tc.T * 2 + rec) * kRec;
-            dst[4 + ttid] = O;
+            rec[4 + ttid] = O;
             if (ttid == 0) {
-                dst[0] = M;
-                dst[1] = L;
+                rec[0] = M;
+                rec[1] = L;
             }
         }
-        ++rec;
-        u += nseg;
     }
 }
 
@@ -1057,13 +1064,11 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     __shared__ float red_s[kConsumerWarps];
     __shared__ __align__(8) unsigned long long bars_s[kTeams][2 * kMaxStages];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // smem (1 KB aligned): [team 0 ring][team 1 ring][xs: H halves][xsum: H/32 floats][merge table][tmp / team scratch]
+    // smem (1 KB aligned): [team 0 ring][team 1 ring][xs: H halves][xsum: H/32 floats][tmp / team scratch]
     const uint32_t ring_bytes = (uint32_t)p.n_stages * kStageBytes;
     __half* xs = reinterpret_cast<__half*>(smem_raw + kTeams * ring_bytes);
     float* xsum = reinterpret_cast<float*>(xs + p.H);
-    unsigned* mt_range = reinterpret_cast<unsigned*>(xsum + p.H / 32);                     // [n_heads]
-    unsigned short* mt_rec = reinterpret_cast<unsigned short*>(mt_range + p.n_heads);      // [teams + n_heads]
-    uint8_t* tmp_raw = reinterpret_cast<uint8_t*>(mt_rec + (gridDim.x * kTeams + p.n_heads));
+    uint8_t* tmp_raw = reinterpret_cast<uint8_t*>(xsum + p.H / 32);
     tmp_raw += (16 - (reinterpret_cast<uintptr_t>(tmp_raw) & 15)) & 15;
     __half* tmp = reinterpret_cast<__half*>(tmp_raw);
 
@@ -1105,8 +1110,6 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     tc.xseg = xs + tc.team * (p.H / 2);
     tc.xsum_seg = xsum + tc.team * (p.H / 64);
     tc.scratch = tmp_raw + tc.team * kTeamScratch;
-    tc.mt_rec = mt_rec;
-    tc.mt_range = mt_range;
     ConsRing ring;
     ring.ring = smem_u32(smem_raw) + tc.team * ring_bytes;
     ring.full = smem_u32(&bars_s[tc.team][0]);
@@ -1128,8 +1131,6 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar + 1) : "memory");
         gen = v;
     }
-
-    build_merge_table(p, nb, mt_rec, mt_range);
 
     // this step's RoPE angles (quant/fused_attn.py:43,91): freq_i = exp(i * inv_base) * pos
     if (blockIdx.x == 0 && tid < 64) {
@@ -1280,8 +1281,7 @@ struct MegaPlan {
 // returns false if the shape does not fit the kernel's staging buffers.
 bool mega_plan(const gptq_llama_model& m, int sms, size_t smem_max, size_t smem_static, MegaPlan& pl) {
     const int H = m.hidden, I = m.intermediate;
-    const size_t table = (size_t)m.n_heads * 4 + (size_t)(sms * kTeams + m.n_heads) * 2;  // attention merge table
-    const size_t fixed = (size_t)H * 2 + (size_t)(H / 32) * 4 + table + 16 + max((size_t)H * 2, (size_t)kTeams * kTeamScratch);
+    const size_t fixed = (size_t)H * 2 + (size_t)(H / 32) * 4 + 16 + max((size_t)H * 2, (size_t)kTeams * kTeamScratch);
     const size_t other = fixed + smem_static + 1024;  // + the kernel's static shared memory + 1 KB alignment slack of the rings
     if (smem_max < other) return false;
     int st = (int)((smem_max - other) / ((size_t)kTeams * kStageBytes));
@@ -1331,7 +1331,7 @@ size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq) {
     (void)max_seq;
     const size_t max_teams = 1024;  // >= kTeams * SM count of any device this library runs on
     return al256((size_t)m.hidden * 2) * 2 + al256((size_t)3 * m.hidden * 4) + al256((size_t)m.hidden * 4) * 2 + al256((size_t)m.intermediate * 4) * 2 +
-           al256(max_teams * 2 * kRec * 4) + al256(128 * 4) + 256;
+           al256(max_teams * kRec * 4) + al256(128 * 4) + 256;
 }
 
 cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream) {
@@ -1379,7 +1379,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     p.acc_d = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
     p.acc_g = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
     p.acc_u = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
-    p.part = reinterpret_cast<float*>(take((size_t)1024 * 2 * kRec * 4));
+    p.part = reinterpret_cast<float*>(take((size_t)1024 * kRec * 4));
     p.rope_cs = reinterpret_cast<float*>(take(128 * 4));
     p.bar = reinterpret_cast<unsigned long long*>(take(256));
     // One tensor map per row stride serves every layer: class 0 = qkv (N = 3H), 1 = o and down (N = H), 2 = gate and up (N = I).
