@@ -2,14 +2,16 @@
 """Headline benchmark: tokens/sec of LLaMA-7B int4 g128 batch-1 decode on B200 (BASELINE.json metric),
 plus the roofline of the dominant kernel and the CPU baseline, as ONE JSON line on rank 0.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm
-    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's arithmetic on the host cores
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 7b|13b-int3|65b|prefill]   # our arm
+    python bench.py --impl reference [--steps K] [--warmup W]                                  # the reference's arithmetic on the host cores
 
-A "step" is one decoded token: one replay of the captured CUDA graph of gptq_llama_decode_step over a
-random-init LLaMA-7B-shaped GPTQ model (32 distinct layers, 3.6 GB of packed weights per step, i.e. far
-larger than the 126 MB L2, so every step streams from HBM) at context position seq-1 = 2047.
-N > 1 (torchrun): the path does not shard at this size ("replicas only"): every rank decodes
-its own sequence on its own GPU, no data-path collective; value = total tokens/s, scaling = weak.
+A "step" is one decoded token: one replay of the captured CUDA graph of gptq_llama_decode_step (ONE persistent kernel) over a
+random-init LLaMA-7B-shaped GPTQ model (32 distinct layers, 3.6 GB of packed weights per step, i.e. far larger than the 126 MB
+L2, so every step streams from HBM) at context position seq-1 = 2047.
+N > 1 (torchrun): the path does not shard at this size ("replicas only"): every rank decodes its own sequence on its
+own GPU, no data-path collective; value = total tokens/s, scaling = weak.
+--config selects the other BASELINE.json configurations (13b-int3 = config 4, 65b = the config-5 model on one GPU, prefill = config 3);
+the default is config 2, the one the metric is quoted on.
 """
 import argparse
 import json
@@ -24,15 +26,36 @@ for p in (ROOT, os.path.join(ROOT, 'gptq-for-llama_b200')):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+
+def _host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if '--impl' in sys.argv and 'reference' in sys.argv:
+    # the CPU arm uses every host core it may run on; torchrun exports OMP_NUM_THREADS=1, which must not leak into it.
+    # (set before torch / libgomp are loaded)
+    os.environ['OMP_NUM_THREADS'] = os.environ.get('BENCH_CPU_THREADS', str(_host_threads()))
+    os.environ.setdefault('OMP_PROC_BIND', 'spread')
+
 import torch  # noqa: E402
 
 METRIC = 'tokens/sec LLaMA-7B int4 g128 batch=1; matvec HBM GB/s vs 8 TB/s roofline'
 SEQ = 2048
-NCU_TRAFFIC_BYTES = 4447960888  # per launch of llama_decode_mega_kernel: 4.4350 GB read + 12.9 MB written (profiles/r1_mega_final_summary.txt)
-BITS, GROUP = 4, 128
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of llama_decode_mega_kernel on the 32-layer model at context 2047
+# (ncu --set full, profiles/r2_mega_summary.txt)
+NCU_TRAFFIC_BYTES = {'7b': None}
+CONFIGS = {  # name -> (size, bits, act_order, BASELINE.json config)
+    '7b': ('7b', 4, False, 'LLaMA-7B int4 g128 batch=1 decode'),
+    '13b-int3': ('13b', 3, True, 'LLaMA-13B int3 g128 act-order batch=1 decode'),
+    '65b': ('65b', 4, False, 'LLaMA-65B int4 g128 batch=1 decode on ONE GPU'),
+}
+GROUP = 128
 
 
-def alg_bytes_qlinear(K, N, M=1, bits=BITS, gs=GROUP):
+def alg_bytes_qlinear(K, N, bits, M=1, gs=GROUP):
     """qweight + scales + qzeros + g_idx + x + out."""
     G = (K + gs - 1) // gs
     return K * N * bits // 8 + G * N * 2 + G * N * bits // 8 + 4 * K + 2 * M * K + 2 * M * N
@@ -41,68 +64,84 @@ def alg_bytes_qlinear(K, N, M=1, bits=BITS, gs=GROUP):
 def measured_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
-        return json.load(open(path)).get('hbm_gbs', 6650.0), 'measured (MEASURED_PEAKS.json)'
-    return 6650.0, 'fallback (B200_PROFILING.md)'
+        d = json.load(open(path))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), d.get('bf16_tflops_sustained', 1400.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 1400.0, 'fallback (B200_PROFILING.md)'
 
 
 # ----------------------------------------------------------------------------------------------------
-# CPU arm: the oracle's restatement of the reference kernels (the reference has no CPU forward), timed on
-# a bounded sample: the quantized linears of ONE decoder layer at M=1, scaled to a 32-layer token.
+# CPU arm: the oracle's C/OpenMP restatement of the reference kernels (the reference has no CPU forward), timed on
+# WHOLE decoded tokens of the same workload: 32 x (RMSNorm, qkv, RoPE-free attention over a 2047-token cache, o_proj, RMSNorm,
+# fused gate/up + SwiGLU, down) + final norm + fp16 lm_head.  One layer's tensors are reused for the 32 layers (they fit the
+# host's last-level cache the second time round, which favours the CPU).
 # ----------------------------------------------------------------------------------------------------
-def cpu_layer_seconds(reps):
-    from oracle import gptq_oracle as O
-    from oracle import cref
-    Q = cref if cref.available() else O  # C/OpenMP restatement (all host threads) when built, else the numpy/torch one
-    hidden, inter = 4096, 11008
-    shapes = {'qkv': (hidden, 3 * hidden), 'o': (hidden, hidden), 'gate': (hidden, inter), 'up': (hidden, inter), 'down': (inter, hidden)}
-    W = {k: O.random_packed(K, N, BITS, GROUP, seed=i)[:4] for i, (k, (K, N)) in enumerate(shapes.items())}
-    x = torch.randn(1, hidden, generator=torch.Generator().manual_seed(0)).half()
-    nw = torch.ones(hidden).half()
+class CpuToken:
+    def __init__(self):
+        from oracle import gptq_oracle as O
+        from oracle import cref
+        self.O = O
+        self.Q = cref if cref.available() else O  # C/OpenMP restatement (all host threads) when built, else the numpy/torch one
+        self.kind = 'C/OpenMP (oracle/qlinear_ref.c)' if cref.available() else 'numpy/torch (oracle/gptq_oracle.py)'
+        self.H, self.I, self.NH, self.V, self.L = 4096, 11008, 32, 32000, 32
+        H, I = self.H, self.I
+        shapes = {'qkv': (H, 3 * H), 'o': (H, H), 'gate': (H, I), 'up': (H, I), 'down': (I, H)}
+        self.W = {k: O.random_packed(K, N, 4, GROUP, seed=i)[:4] for i, (k, (K, N)) in enumerate(shapes.items())}
+        g = torch.Generator().manual_seed(0)
+        self.x = torch.randn(1, H, generator=g).half()
+        self.nw = torch.ones(H).half()
+        self.kc = (torch.randn(self.NH, SEQ, H // self.NH, generator=g) * 0.5).half()
+        self.vc = (torch.randn(self.NH, SEQ, H // self.NH, generator=g) * 0.5).half()
+        self.lm_head = (torch.randn(self.V, H, generator=g) * 0.02).half()
 
-    def layer():
-        h = O.rmsnorm_fwd(x, nw, 1e-6)
-        Q.qlinear_fwd(h, *W['qkv'], BITS)
-        Q.qlinear_fwd(x, *W['o'], BITS)
-        mid = Q.fused_mlp_fwd(h, W['gate'], W['up'], BITS)
-        Q.qlinear_fwd(mid, *W['down'], BITS)
+    def token(self):
+        O, Q, W, H, NH = self.O, self.Q, self.W, self.H, self.NH
+        x = self.x
+        for _ in range(self.L):
+            qkv = Q.qlinear_fwd(O.rmsnorm_fwd(x, self.nw, 1e-6), *W['qkv'], 4).view(3, NH, H // NH)
+            s = torch.einsum('hd,htd->ht', qkv[0].float(), self.kc.float()) * (H // NH)**-0.5
+            att = torch.einsum('ht,htd->hd', torch.softmax(s, -1), self.vc.float()).half().reshape(1, H)
+            x = x + Q.qlinear_fwd(att, *W['o'], 4)
+            mid = Q.fused_mlp_fwd(O.rmsnorm_fwd(x, self.nw, 1e-6), W['gate'], W['up'], 4)
+            x = (x + Q.qlinear_fwd(mid, *W['down'], 4)) * 0.5  # keep the synthetic residual bounded
+        return O.rmsnorm_fwd(x, self.nw, 1e-6).float() @ self.lm_head.float().t()
 
-    layer()
-    ts = []
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        layer()
-        ts.append(time.perf_counter() - t0)
-    return statistics.median(ts)
+    def time_tokens(self, steps, warmup):
+        for _ in range(warmup):
+            self.token()
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            self.token()
+            ts.append(time.perf_counter() - t0)
+        return ts
 
 
-def cpu_baseline(reps=5):
-    t_layer = cpu_layer_seconds(reps)
-    n_layers = 32
+def cpu_baseline(steps=2, warmup=1):
+    c = CpuToken()
+    ts = c.time_tokens(steps, warmup)
+    t = statistics.median(ts)
+    threads = int(os.environ.get('OMP_NUM_THREADS', _host_threads()))
     return {
-        'value': 1.0 / (t_layer * n_layers),
-        'unit': 'tokens/s',
-        'cores': os.cpu_count(),
-        'kind': 'port',
-        'sample': f'oracle C/OpenMP restatement of matmul_248/fusedmatmul_248 (oracle/qlinear_ref.c, all host threads) on the 5 quantized linears of 1 of 32 LLaMA-7B layers at M=1, '
-                  f'median of {reps} passes ({t_layer:.3f} s/layer) x 32 layers; lm_head and attention excluded (favours the CPU)',
-    }, t_layer
+        'value': 1.0 / t, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
+        'sample': f'oracle {c.kind} restatement of matmul_248 / fusedmatmul_248 on {threads} host threads: {steps} WHOLE decoded tokens (32 layers x 5 quantized linears at '
+                  f'M=1 + attention over 2047 cached tokens + fp16 lm_head), median {t:.2f} s/token; one layer\'s tensors reused for all 32 layers',
+    }, ts
 
 
 def run_reference(args):
-    """`--impl reference`: the reference's own arithmetic on the host cores (torch threads = all cores)."""
+    """`--impl reference`: the reference's own arithmetic on the host cores, rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warm = max(1, args.steps), max(0, args.warmup)
-    reps = min(max(steps, 1), 20)
-    for _ in range(min(warm, 1)):
-        cpu_layer_seconds(1)
-    base, t_layer = cpu_baseline(reps)
-    ms = t_layer * 32 * 1e3
+    torch.set_num_threads(int(os.environ['OMP_NUM_THREADS']))
+    steps = min(max(1, args.steps), 12)  # bounded sample: ~3 s per token on 128 threads
+    warm = min(max(0, args.warmup), 2)
+    base, ts = cpu_baseline(steps, warm)
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': reps, 'warmup': min(warm, 1),
-        'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
-        'config': {'workload': f'LLaMA-7B int4 g128 batch=1 decode, seq={SEQ}', 'note': 'CPU: bounded sample (1 layer x 32)'},
+        'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
+        'ms_per_step': statistics.mean(ts) * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': f'LLaMA-7B int4 g128 batch=1 decode, context {SEQ - 1} (seq={SEQ}), 32 layers, random-init packed weights',
+                   'note': f'CPU arm: steps bounded to {steps} whole tokens (requested {args.steps}); same workload as the GPU arm'},
         'cpu_baseline': base,
         'e2e': {'value': base['value'], 'unit': 'tokens/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -132,7 +171,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for ln in out.strip().splitlines():
             f = [t.strip() for t in ln.split(',')]
             if len(f) < 7:
@@ -140,12 +179,14 @@ class ClockSampler:
             try:
                 sm.append(float(f[0]))
                 mx.append(float(f[1]))
+                pw.append(float(f[2]))
             except ValueError:
                 continue
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
-        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+        return {'sm_mhz': statistics.median(sm) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'power_w_max': max(pw) if pw else None, 'samples': len(sm),
+                'reasons': sorted(reasons)}
 
 
 def timed(fn, steps, dist_on):
@@ -165,7 +206,7 @@ def timed(fn, steps, dist_on):
     return a.elapsed_time(b) / 1e3
 
 
-def run_ours(args):
+def run_decode(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -177,8 +218,9 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=dev)
     from gptq_b200 import engine, ops
 
+    size, bits, act, title = CONFIGS[args.config]
     steps, warm = max(1, args.steps), max(3, args.warmup)
-    dec = engine.synthetic_llama('7b', bits=BITS, groupsize=GROUP, device=str(dev), seed=rank, max_seq=SEQ)
+    dec = engine.synthetic_llama(size, bits=bits, groupsize=GROUP, act_order=act, device=str(dev), seed=rank, max_seq=SEQ)
     # synthetic context: the cache holds seq-1 = 2047 tokens of random K/V; the step decodes token 2048
     dec.k_cache.normal_(0, 0.5)
     dec.v_cache.normal_(0, 0.5)
@@ -189,6 +231,8 @@ def run_ours(args):
     # ---- device-resident arm: inputs already in HBM ------------------------------------------------
     for _ in range(warm):
         dec.step()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(dec.logits).all()), 'non-finite logits'
     sampler = ClockSampler(local) if rank == 0 else None
     t_dev = timed(dec.step, steps, dist_on)
 
@@ -210,29 +254,30 @@ def run_ours(args):
     t_e2e = timed(e2e_step, steps, dist_on)
     clocks = sampler.stop() if sampler else None
 
-    # ---- dominant kernel in isolation: fused gate/up matvec over the 32 layers' distinct weights ------
-    x = torch.randn(1, dec.hidden, device=dev).half()
-    gates = [(ly['gate'], ly['up']) for ly in dec.layers]
+    # ---- the drop-in op in isolation: standalone fused gate/up matvec (gptq_fused_mlp_fwd) over the layers' distinct weights ------
+    mlp = None
+    if bits == 4 and not act:
+        x = torch.randn(1, dec.hidden, device=dev).half()
+        gates = [(ly['gate'], ly['up']) for ly in dec.layers]
 
-    def mlp_all():
-        for g, u in gates:
-            ops.fused_mlp(x, (g.qweight, g.scales, g.qzeros, g.g_idx), (u.qweight, u.scales, u.qzeros, u.g_idx), BITS, GROUP)
+        def mlp_all():
+            for g, u in gates:
+                ops.fused_mlp(x, (g.qweight, g.scales, g.qzeros, g.g_idx), (u.qweight, u.scales, u.qzeros, u.g_idx), bits, GROUP)
 
-    side = torch.cuda.Stream()
-    with torch.cuda.stream(side):
-        mlp_all()
-        side.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
             mlp_all()
-    torch.cuda.synchronize()
-    for _ in range(3):
-        graph.replay()
-    reps = 10
-    t_k = timed(graph.replay, reps, False) / (reps * len(gates))
-    kbytes = 2 * alg_bytes_qlinear(dec.hidden, dec.intermediate) - 2 * dec.hidden  # two weights, x read once
-    peak, peak_src = measured_peaks()
-    achieved = kbytes / t_k / 1e9
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                mlp_all()
+        torch.cuda.synchronize()
+        for _ in range(3):
+            graph.replay()
+        reps = 10
+        t_k = timed(graph.replay, reps, False) / (reps * len(gates))
+        kbytes = 2 * alg_bytes_qlinear(dec.hidden, dec.intermediate, bits) - 2 * dec.hidden  # two weights, x read once
+    peak, _, _, peak_src = measured_peaks()
 
     # max over ranks, whole-job aggregate
     tt = torch.tensor([t_dev, t_e2e], device=dev, dtype=torch.float64)
@@ -240,15 +285,22 @@ def run_ours(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = tt.tolist()
     if rank == 0:
-        base, _ = cpu_baseline(5) if world == 1 else (None, None)
+        base, _ = cpu_baseline(2, 1) if (world == 1 and args.config == '7b') else (None, None)
+        H, I, V, L = dec.hidden, dec.intermediate, dec.vocab, len(dec.layers)
+        # algorithmic bytes per token: quant linears of the CHECKPOINT (not of derived buffers) + fp16 lm_head + KV cache read at this context
+        per_layer = alg_bytes_qlinear(H, 3 * H, bits) + alg_bytes_qlinear(H, H, bits) + 2 * alg_bytes_qlinear(H, I, bits) + alg_bytes_qlinear(I, H, bits)
+        kv = 2 * L * SEQ * H * 2
+        step_bytes = L * per_layer + V * H * 2 + kv
+        t_step = t_dev / steps
         line = {
-            'metric': METRIC, 'value': world * steps / t_dev, 'unit': 'tokens/s', 'n_gpus': world, 'steps': steps, 'warmup': warm,
-            'ms_per_step': t_dev / steps * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+            'metric': METRIC if args.config == '7b' else f'tokens/sec {title}', 'value': world * steps / t_dev, 'unit': 'tokens/s', 'n_gpus': world, 'steps': steps,
+            'warmup': warm, 'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
             'config': {
-                'workload': f'LLaMA-7B int4 g128 batch=1 decode, context {pos} (seq={SEQ}), 32 layers, random-init packed weights',
+                'workload': f'{title}, context {pos} (seq={SEQ}), {L} layers, random-init packed weights',
                 'parallelism': 'replicas only (one independent sequence per GPU, no data-path collective)' if world > 1 else 'single GPU',
-                'l2': 'each step streams 3.6 GB of weights + 1.07 GB of KV cache (inputs >> 126 MB L2); no explicit flush needed',
-                'arithmetic': 'int4 weights dequantised to fp16 exactly as the reference kernel, fp16 x fp16 -> fp32 accumulate, fp16 store',
+                'l2': f'each step streams {L * per_layer / 1e9:.1f} GB of weights + {kv / 1e9:.2f} GB of KV cache (inputs >> 126 MB L2); no explicit flush needed',
+                'arithmetic': 'raw int4 nibbles x fp16 activations on the tensor pipe (mma.sync, exact products, fp32 accumulate), fp16 scale and zero applied once per '
+                              'quantisation group on the fp32 accumulator, fp16 store; within 1e-3 of the reference kernel (tests/)',
             },
             'e2e': {'value': world * steps / t_e2e, 'unit': 'tokens/s', 'h2d_bytes_per_step': 8, 'd2h_bytes_per_step': dec.vocab * 2,
                     'note': 'host token+position (pinned) -> H2D -> CUDA-graph decode step -> D2H fp16 logits, synchronised every step'},
@@ -256,32 +308,67 @@ def run_ours(args):
             'roofline': None,
             'clocks': clocks,
         }
-        # algorithmic bytes per token: 32 x quant linears + fp16 lm_head + KV cache read at this context
-        H, I, V = dec.hidden, dec.intermediate, dec.vocab
-        per_layer = alg_bytes_qlinear(H, 3 * H) + alg_bytes_qlinear(H, H) + 2 * alg_bytes_qlinear(H, I) + alg_bytes_qlinear(I, H)
-        kv = 2 * 32 * SEQ * H * 2
-        step_bytes = 32 * per_layer + V * H * 2 + kv
-        t_step = t_dev / steps
-        mlp = {'kernel': 'qmatvec_int4_kernel<dual> (standalone gptq_fused_mlp_fwd, 4096->11008 x2, timed alone over 32 distinct layers)',
-               'achieved': achieved, 'frac': achieved / peak, 'bytes_per_launch': kbytes, 'us_per_launch': t_k * 1e6}
-        if dec.launches_per_step() == 1:
-            # the whole token is ONE persistent kernel: its launch duration is the step time measured above with CUDA events
-            line['roofline'] = {'bound': 'hbm', 'kernel': 'llama_decode_mega_kernel (persistent decode step: 160 int4 matvecs + attention + lm_head)',
-                                'achieved': step_bytes / t_step / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': step_bytes / t_step / 1e9 / peak,
-                                'peak_source': peak_src, 'bytes_per_launch': step_bytes, 'us_per_launch': t_step * 1e6,
-                                'frac_of_8TBs': step_bytes / t_step / 8e12,
-                                'traffic': NCU_TRAFFIC_BYTES, 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/',
-                                'standalone_fused_mlp': mlp}
-        else:
-            line['roofline'] = {'bound': 'hbm', 'kernel': mlp['kernel'], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                                'peak_source': peak_src, 'bytes_per_launch': kbytes, 'us_per_launch': t_k * 1e6, 'frac_of_8TBs': achieved / 8000.0,
-                                'traffic': None, 'step_bytes': step_bytes, 'step_achieved_gbs': step_bytes / t_step / 1e9,
-                                'step_frac': step_bytes / t_step / 1e9 / peak}
+        assert dec.launches_per_step() == 1, 'the persistent kernel must be the measured path'
+        # the whole token is ONE persistent kernel: its launch duration is the step time measured above with CUDA events
+        line['roofline'] = {'bound': 'hbm', 'kernel': 'llama_decode_mega_kernel (persistent decode step: all quantized matvecs + attention + lm_head of a token)',
+                            'achieved': step_bytes / t_step / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': step_bytes / t_step / 1e9 / peak, 'peak_source': peak_src,
+                            'bytes_per_launch': step_bytes, 'us_per_launch': t_step * 1e6, 'frac_of_8TBs': step_bytes / t_step / 8e12,
+                            'traffic': NCU_TRAFFIC_BYTES.get(args.config), 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/'}
+        if mlp is None and bits == 4 and not act:
+            ach = kbytes / t_k / 1e9
+            line['roofline']['standalone_fused_mlp'] = {'kernel': 'qmatvec_int4_kernel<dual> (standalone gptq_fused_mlp_fwd, timed alone over the layers\' distinct weights)',
+                                                        'achieved': ach, 'frac': ach / peak, 'bytes_per_launch': kbytes, 'us_per_launch': t_k * 1e6}
+        ref_path = os.path.join(ROOT, 'profiles', 'r2_reference_triton_decode.json')
+        if args.config == '7b' and os.path.exists(ref_path):
+            try:
+                rt = json.loads(open(ref_path).readline())
+                line['reference_triton'] = {'tokens_per_s': rt['tokens_per_s'], 'ms_per_token': rt['ms_per_token'],
+                                            'source': 'profiles/r2_reference_triton_decode.json: the unmodified reference modules (Triton kernels) on a B200 of this pool, '
+                                                      'measured separately by tools/refshim/ref_decode_bench.py; not re-measured in this run'}
+            except (ValueError, KeyError):
+                pass
         if base is not None:
             line['cpu_baseline'] = base
         print(json.dumps(line))
     if dist_on:
         dist.destroy_process_group()
+
+
+def run_prefill(args):
+    """BASELINE.json config 3: LLaMA-7B int4 g128 prefill, batch 32 x seq 2048 (M = 65536): a step = the quantized linears of one decoder
+    layer on the tcgen05 GEMM path (qkv, o, fused gate/up + SwiGLU, down); tokens/s counts the 32 layers' linears only."""
+    from gptq_b200 import engine, ops
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    M, H, I = 65536, 4096, 11008
+    gen = torch.Generator(device=dev).manual_seed(0)
+    L = {k: engine.random_qlayer(K, N, 4, GROUP, dev, gen) for k, (K, N) in {'qkv': (H, 3 * H), 'o': (H, H), 'gate': (H, I), 'up': (H, I), 'down': (I, H)}.items()}
+    t4 = lambda w: (w.qweight, w.scales, w.qzeros, w.g_idx)
+    x = torch.randn(M, H, device=dev, generator=gen).half()
+
+    def layer():
+        ops.matmul248(x, *t4(L['qkv']), 4, None, groupsize=GROUP)
+        ops.matmul248(x, *t4(L['o']), 4, None, groupsize=GROUP)
+        h = ops.fused_mlp(x, t4(L['gate']), t4(L['up']), 4, GROUP)
+        ops.matmul248(h, *t4(L['down']), 4, None, groupsize=GROUP)
+
+    steps, warm = max(1, min(args.steps, 20)), max(3, min(args.warmup, 5))
+    for _ in range(warm):
+        layer()
+    sampler = ClockSampler(dev.index)
+    t = timed(layer, steps, False) / steps
+    clocks = sampler.stop()
+    flops = 2 * M * (H * 3 * H + H * H + 2 * H * I + I * H)
+    _, burst, sustained, src = measured_peaks()
+    print(json.dumps({
+        'metric': 'prefill tokens/sec LLaMA-7B int4 g128 batch=32 seq=2048 (quantized linears, tcgen05 GEMM path)', 'value': M / (t * 32), 'unit': 'tokens/s', 'n_gpus': 1,
+        'steps': steps, 'warmup': warm, 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': 'LLaMA-7B int4 g128 prefill batch 32 x seq 2048 (M=65536): the 4 quantized linears of one decoder layer per step; tokens/s = M / (32 x step)',
+                   'l2': 'activations 0.5-1.4 GB per operand (>> 126 MB L2)'},
+        'gpu_launches': 4 * steps, 'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'kernel': 'qgemm_tcgen05_kernel', 'achieved': flops / t / 1e12, 'peak': sustained, 'unit': 'TFLOP/s', 'frac': flops / t / 1e12 / sustained,
+                     'frac_of_burst': flops / t / 1e12 / burst, 'peak_source': src + ' (sustained cuBLAS bf16)', 'traffic': None},
+    }))
 
 
 def main():
@@ -290,11 +377,14 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='7b', choices=sorted(CONFIGS) + ['prefill'])
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif args.config == 'prefill':
+        run_prefill(args)
     else:
-        run_ours(args)
+        run_decode(args)
 
 
 if __name__ == '__main__':

@@ -38,11 +38,11 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-__global__ void embed_kernel(const __half* __restrict__ embed, const int32_t* __restrict__ tokens, __half* __restrict__ x, int hidden) {
+__global__ void embed_kernel(const __half* __restrict__ embed, const int32_t* __restrict__ tokens, __half* __restrict__ x, int hidden, int vocab) {
     const int b = blockIdx.x;
     pdl_trigger();
     pdl_wait();
-    const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tokens[b] * hidden);
+    const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)min(max(tokens[b], 0), vocab - 1) * hidden);
     uint4* dst = reinterpret_cast<uint4*>(x + (size_t)b * hidden);
     for (int i = threadIdx.x; i < hidden / 8; i += blockDim.x) dst[i] = __ldg(src + i);
 }
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kAttnThreads) attn_decode_kernel(const __half*
     const int head = blockIdx.x, split = blockIdx.y, b = blockIdx.z;
     pdl_trigger();
     pdl_wait();
-    const int pos = positions[b];
+    const int pos = min(max(positions[b], 0), max_seq - 1);  // the host rejects positions outside the cache; never write past it
     const int T = pos + 1;
     const int c0 = split * kAttnChunk;
     if (c0 >= T) return;
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kHeadDim) attn_combine_kernel(const float* __r
     const int head = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
     pdl_trigger();
     pdl_wait();
-    const int nvalid = min(nsplit, positions[b] / kAttnChunk + 1);
+    const int nvalid = min(nsplit, max(positions[b], 0) / kAttnChunk + 1);
     const float* src = part + ((size_t)(b * n_heads + head) * nsplit) * (kHeadDim + 2);
     float M = -INFINITY;
     for (int s = 0; s < nvalid; ++s) M = fmaxf(M, src[(size_t)s * (kHeadDim + 2)]);
@@ -469,7 +469,7 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
         if ((expr) != cudaSuccess) return GPTQ_ERR_CUDA; \
     } while (0)
 
-    GPTQ_TRY(launch_pdl(embed_kernel, dim3(B), dim3(256), 0, stream, reinterpret_cast<const __half*>(m.embed), st->tokens, x, H));
+    GPTQ_TRY(launch_pdl(embed_kernel, dim3(B), dim3(256), 0, stream, reinterpret_cast<const __half*>(m.embed), st->tokens, x, H, m.vocab));
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         GPTQ_TRY(engine_linear(ly.qkv, nullptr, x, H, ly.input_norm, m.rms_eps, nullptr, qkv, 3 * H, B, sc, L, stream));

@@ -201,10 +201,27 @@ class LlamaDecoder:
     def reset(self):
         self.positions.zero_()
 
+    def set_input(self, tokens, position):
+        """Token ids (int or sequence of `batch` ints) and the cache position of this step; validated on the host: the kernels
+        only clamp (a position beyond the cache or a token outside the vocabulary must never reach them)."""
+        toks = [int(tokens)] * self.batch if isinstance(tokens, int) else [int(t) for t in tokens]
+        if len(toks) != self.batch:
+            raise ValueError(f'expected {self.batch} token ids, got {len(toks)}')
+        if not 0 <= int(position) < self.max_seq:
+            raise ValueError(f'position {position} outside the KV cache (max_seq = {self.max_seq})')
+        if any(t < 0 or t >= self.vocab for t in toks):
+            raise ValueError(f'token id outside the vocabulary (0..{self.vocab - 1})')
+        self.tokens.copy_(torch.tensor(toks, dtype=torch.int32))
+        self.positions.fill_(int(position))
+
     @torch.no_grad()
     def generate(self, prompt_ids, max_new_tokens):
         """Greedy decode (batch 1): the prompt is fed token by token through the same decode step."""
         assert self.batch == 1
+        if len(prompt_ids) < 1 or len(prompt_ids) + max_new_tokens > self.max_seq + 1:
+            raise ValueError(f'prompt ({len(prompt_ids)}) + max_new_tokens ({max_new_tokens}) does not fit the KV cache (max_seq = {self.max_seq})')
+        if any(int(t) < 0 or int(t) >= self.vocab for t in prompt_ids):
+            raise ValueError(f'prompt token id outside the vocabulary (0..{self.vocab - 1})')
         out = list(prompt_ids)
         self.reset()
         tok = torch.empty(1, dtype=torch.int32, device=self.dev)

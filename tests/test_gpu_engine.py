@@ -114,3 +114,28 @@ def test_batched_decode_matches_single():
             d1.step()
         torch.cuda.synchronize()
         assert_rel_close(batched[b], d1.logits[0], rel=1e-2, what=f'batch row {b}')
+
+
+def test_host_rejects_positions_and_tokens_outside_the_cache_and_vocabulary():
+    """The kernels index the KV cache with the step's position and the embedding with the token id: the host API validates both
+    (ADVICE r1), the kernels clamp as a last line of defence."""
+    from gptq_b200 import engine
+    dec = engine.synthetic_llama('tiny256', bits=4, groupsize=64, vocab=300, seed=4, max_seq=16)
+    with pytest.raises(ValueError):
+        dec.generate([1, 2, 3], 15)  # 3 + 15 - 1 positions > max_seq
+    with pytest.raises(ValueError):
+        dec.generate([1, 300], 2)
+    with pytest.raises(ValueError):
+        dec.set_input(5, 16)
+    with pytest.raises(ValueError):
+        dec.set_input(-1, 0)
+    out = dec.generate([1, 2, 3], 14)  # exactly fills the cache
+    assert len(out) == 17
+    # a raw out-of-range position is clamped by the kernel instead of writing past the cache
+    guard = dec.k_cache.clone()
+    dec.tokens.fill_(7)
+    dec.positions.fill_(10_000)
+    dec.step()
+    torch.cuda.synchronize()
+    assert torch.isfinite(dec.logits).all()
+    assert torch.equal(dec.k_cache[:, :, :, :15], guard[:, :, :, :15])  # only the last row may have been rewritten
