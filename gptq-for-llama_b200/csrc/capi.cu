@@ -1,5 +1,7 @@
 // extern "C" surface of libgptq_b200.so: argument validation, error codes, kernel dispatch.
 // No torch types, no allocation, no synchronisation, no global mutable state.
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -146,6 +148,29 @@ int gptq_unpack_qweight(const int32_t* qweight, int32_t* intweight, int K, int N
 int gptq_unpack_qzeros(const int32_t* qzeros, int32_t* zeros_m1, int G, int N, int bits, gptq_stream_t stream) {
     return pack_common(qzeros, zeros_m1, N, G, bits, true, false, stream);
 }
+
+int gptq_ipc_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    if (ptr == nullptr || handle == nullptr || bytes == 0) return GPTQ_ERR_NULL;
+    void* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) return GPTQ_ERR_CUDA;
+    cudaIpcMemHandle_t h;
+    if (cudaMemset(d, 0, bytes) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess || cudaIpcGetMemHandle(&h, d) != cudaSuccess) {
+        cudaFree(d);
+        return GPTQ_ERR_CUDA;
+    }
+    memcpy(handle, &h, 64);
+    *ptr = d;
+    return GPTQ_OK;
+}
+int gptq_ipc_open(const unsigned char handle[64], void** ptr) {
+    if (ptr == nullptr || handle == nullptr) return GPTQ_ERR_NULL;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    return cuda_status(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+}
+int gptq_ipc_close(void* ptr) { return ptr == nullptr ? GPTQ_ERR_NULL : cuda_status(cudaIpcCloseMemHandle(ptr)); }
+int gptq_ipc_free(void* ptr) { return ptr == nullptr ? GPTQ_ERR_NULL : cuda_status(cudaFree(ptr)); }
 
 int gptq_dequant(const gptq_qweight* w, void* out, int64_t ldo, gptq_stream_t stream) {
     if (int st = check_weight(w)) return st;

@@ -398,7 +398,7 @@ extern "C" size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int ba
 
 extern "C" size_t gptq_llama_persistent_scratch_offset(const gptq_llama_model* model, int batch, int max_seq) {
     if (model == nullptr || batch < 1 || batch > 8 || max_seq < 1) return 0;
-    return scratch_layout(*model, batch, max_seq).mega;
+    return scratch_layout(*model, batch, max_seq).mega;  // (0 for a tensor-parallel state)
 }
 
 static bool has_input_perm(const gptq_llama_model& m) {
@@ -432,14 +432,15 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
     if (st->k_cache == nullptr || st->v_cache == nullptr || st->tokens == nullptr || st->positions == nullptr || st->logits == nullptr || st->scratch == nullptr)
         return GPTQ_ERR_NULL;
     if (m.head_dim != kHeadDim) return GPTQ_ERR_UNSUPPORTED;  // LLaMA-7B/13B/33B/65B all use head_dim 128
-    if (m.n_heads * m.head_dim != m.hidden || m.hidden % 32 != 0 || m.intermediate % 32 != 0 || m.n_layers < 1 || m.vocab < 1) return GPTQ_ERR_SHAPE;
+    const int Hq = m.n_heads * m.head_dim;  // = hidden, or this rank's share of it under tensor parallelism
+    if ((st->tp == nullptr && Hq != m.hidden) || Hq < 1 || Hq > m.hidden || m.hidden % 32 != 0 || m.intermediate % 32 != 0 || m.n_layers < 1 || m.vocab < 1) return GPTQ_ERR_SHAPE;
     if (st->batch < 1 || st->batch > 8 || st->max_seq < 1) return GPTQ_ERR_SHAPE;
     const ScratchLayout L = scratch_layout(m, st->batch, st->max_seq);
     if (st->scratch_bytes < L.total) return GPTQ_ERR_WORKSPACE;
     if ((reinterpret_cast<uintptr_t>(st->scratch) & 255) != 0) return GPTQ_ERR_ALIGN;
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
-        if (ly.qkv.K != m.hidden || ly.qkv.N != 3 * m.hidden || ly.o.K != m.hidden || ly.o.N != m.hidden || ly.gate.K != m.hidden ||
+        if (ly.qkv.K != m.hidden || ly.qkv.N != 3 * Hq || ly.o.K != Hq || ly.o.N != m.hidden || ly.gate.K != m.hidden ||
             ly.gate.N != m.intermediate || ly.up.K != m.hidden || ly.up.N != m.intermediate || ly.down.K != m.intermediate || ly.down.N != m.hidden)
             return GPTQ_ERR_SHAPE;
         if (ly.input_norm == nullptr || ly.post_norm == nullptr) return GPTQ_ERR_NULL;
@@ -448,12 +449,13 @@ extern "C" int gptq_llama_decode_step(const gptq_llama_model* model, const gptq_
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     uint8_t* sc = reinterpret_cast<uint8_t*>(st->scratch);
     if (mega_supported(m, *st)) {
-        const cudaError_t e = launch_decode_mega(m, *st, sc + L.mega, stream);
+        // tensor-parallel ranks keep the persistent kernel's region at the START of the scratch area (peers address it by offset)
+        const cudaError_t e = launch_decode_mega(m, *st, st->tp != nullptr ? sc : sc + L.mega, stream);
         if (e == cudaSuccess) return GPTQ_OK;
         if (e != cudaErrorCooperativeLaunchTooLarge && e != cudaErrorInvalidConfiguration) return GPTQ_ERR_CUDA;
         // the device cannot co-schedule the persistent grid (or the shape does not fit its staging buffers): per-op kernel chain below
     }
-    if (has_input_perm(m)) return GPTQ_ERR_UNSUPPORTED;
+    if (has_input_perm(m) || st->tp != nullptr) return GPTQ_ERR_UNSUPPORTED;  // only the persistent kernel implements these
     __half* x = reinterpret_cast<__half*>(sc + L.x);
     __half* qkv = reinterpret_cast<__half*>(sc + L.qkv);
     __half* attn = reinterpret_cast<__half*>(sc + L.attn);

@@ -127,8 +127,12 @@ struct LayerDesc {
     const int32_t* o_perm;
     const int32_t* mlp_perm;
 };
+constexpr int kMaxTP = 8;
 struct MegaParams {
-    int n_layers, H, I, V, n_heads, max_seq, n_stages, lm_rows;
+    // H: hidden size (the residual stream, replicated under tensor parallelism); n_heads, Hq = 128 * n_heads, I: this rank's attention heads
+    // / attention width / MLP width (the full ones on a single GPU); V: vocabulary, [v0, v1): the lm_head rows of this rank
+    int n_layers, H, Hq, I, V, v0, v1, n_heads, max_seq, n_stages, lm_rows;
+    int tp_size, tp_rank;
     float eps, inv_base, scale;
     const __half* embed;
     const __half* final_norm;
@@ -150,6 +154,13 @@ struct MegaParams {
     float* part;       // [teams][kRec]  attention partial records (m, l, pad, pad, o[128]), one per team and layer
     float* rope_cs;    // [128]: cos[64], sin[64] of this step's position
     unsigned long long* bar;  // [0]: monotonic arrival counter of the grid barrier, [1]: its value when the previous launch ended
+    // tensor parallelism (tp_size > 1): the o_proj / down_proj partial sums of every rank are RED-added into EVERY rank's accumulator over
+    // NVLink (peer pointers), the lm_head slices are stored into every rank's logits, and the three hand-offs that follow them use
+    // a cross-GPU barrier: xbar = this rank's arrival counters, one 256-byte line per source rank, line kMaxTP = value at launch end
+    float* acc_o_peer[kMaxTP];
+    float* acc_d_peer[kMaxTP];
+    __half* logits_peer[kMaxTP];
+    unsigned long long* xbar_peer[kMaxTP];
     LayerDesc layers[kMaxLayers];
     CUtensorMap tmaps[6];  // [class]: 16-row boxes (a full stage), [3 + class]: 4-row boxes (one k-step)
 };
@@ -298,10 +309,11 @@ __device__ void produce_kv(ProdRing& r, const MegaParams& p, int layer, unsigned
 __device__ void produce_lm_head(ProdRing& r, const MegaParams& p, unsigned T, unsigned nb) {
     const int R = p.lm_rows;
     int u, u1;
-    team_range(T, (unsigned)((p.V + R - 1) / R), nb, u, u1);
+    const int nloc = p.v1 - p.v0;
+    team_range(T, (unsigned)((nloc + R - 1) / R), nb, u, u1);
 #pragma unroll 1
     for (; u < u1; ++u) {
-        const int nrows = min(R, p.V - u * R);
+        const int nrows = min(R, nloc - u * R);
         uint32_t bar;
         const uint32_t dst = prod_acquire(r, bar);
         const uint32_t bytes = (uint32_t)nrows * p.H * 2;
@@ -317,12 +329,12 @@ __device__ void producer_loop(const MegaParams& p, ProdRing r, unsigned T, unsig
         const LayerDesc& L = p.layers[l];
         {
             const MatDesc* const md[1] = {&L.qkv};
-            produce_matvec<1>(r, p, md, p.H, 3 * p.H, T, nb);
+            produce_matvec<1>(r, p, md, p.H, 3 * p.Hq, T, nb);
         }
         produce_kv(r, p, l, T, nb);
         {
             const MatDesc* const md[1] = {&L.o};
-            produce_matvec<1>(r, p, md, p.H, p.H, T, nb);
+            produce_matvec<1>(r, p, md, p.Hq, p.H, T, nb);
         }
         {
             const MatDesc* const md[2] = {&L.gate, &L.up};
@@ -390,6 +402,26 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
 #ifdef GPTQ_BARRIER_FENCE
         fence_acq_rel_gpu();
 #endif
+    }
+    cta_sync();
+}
+
+// Cross-GPU barrier of all CTAs of all tensor-parallel ranks: every CTA adds 1 to ITS source line of every rank's counter block
+// (system-scope release after a system fence, so its remote REDs are visible first) and polls its own rank's lines.
+__device__ __forceinline__ void tp_barrier(const MegaParams& p, unsigned long long& target) {
+    cta_sync();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        for (int q = 0; q < p.tp_size; ++q)
+            asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(p.xbar_peer[q] + 32 * p.tp_rank) : "memory");
+        const unsigned long long* mine = p.xbar_peer[p.tp_rank];
+        for (int q = 0; q < p.tp_size; ++q) {
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + 32 * q) : "memory");
+            } while (v < target);
+        }
     }
     cta_sync();
 }
@@ -730,9 +762,10 @@ __device__ void stage_range(const MegaParams& p, const TeamCtx& tc, int nk, int 
 
 // One matvec op for this team: consume the stages of its unit range from the ring, RED the results.
 // NM = 2: gate|up as one virtual matrix (out0 = gate accumulators, out1 = up accumulators).
+// peers != nullptr (tensor parallelism, o_proj / down_proj): the result is RED-added into out0's counterpart on every rank.
 template <int NM, int XMODE, bool ACT = false>
 __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, int gs_steps, int K, int N, float* out0, float* out1, const __half* xs_full,
-                           const float* xsum_full, const int32_t* perm = nullptr) {
+                           const float* xsum_full, const int32_t* perm = nullptr, float* const* peers = nullptr) {
     const int lane = tc.lane, g = lane >> 2, t = lane & 3;
     const int nk = K / 32, nslab = N / kSlabCols;
     int u, u_end;
@@ -830,7 +863,12 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
             gpos += n;
             if (gpos == gs_steps) gpos = 0;
         }
-        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(outp), "f"(tot) : "memory");  // the warp's 32 columns: one 128-byte line
+        if (peers == nullptr || p.tp_size == 1) {
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(outp), "f"(tot) : "memory");  // the warp's 32 columns: one 128-byte line
+        } else {
+            const size_t off = (size_t)(outp - out0);
+            for (int q = 0; q < p.tp_size; ++q) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(peers[q] + off), "f"(tot) : "memory");
+        }
         u += nseg;
     }
 }
@@ -874,8 +912,8 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
             const float qr = hi ? __fadd_rn(__fmul_rn(qx, s), __fmul_rn(qy, c)) : __fsub_rn(__fmul_rn(qx, c), __fmul_rn(qy, s));
             q_s[ttid] = __half2float(__float2half_rn(qr));
             if (owns_new) {  // this segment owns the new key/value: RoPE(k), append both to the cache
-                const float* ak = aq + p.H;
-                const float* av = aq + 2 * p.H;
+                const float* ak = aq + p.Hq;
+                const float* av = aq + 2 * p.Hq;
                 const float kx = __half2float(__float2half_rn(ld_cg(ak + i))), ky = __half2float(__float2half_rn(ld_cg(ak + i + 64)));
                 const float kr = hi ? __fadd_rn(__fmul_rn(kx, s), __fmul_rn(ky, c)) : __fsub_rn(__fmul_rn(kx, c), __fmul_rn(ky, s));
                 const __half kh = __float2half_rn(kr), vh = __float2half_rn(ld_cg(av + ttid));
@@ -998,7 +1036,8 @@ __device__ void run_attention(const MegaParams& p, ConsRing& ring, const TeamCtx
 __device__ void run_lm_head(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, const __half* xs_plain) {
     const int R = p.lm_rows, H = p.H, nch = H / 8;
     int u, u_end;
-    team_range(tc.T, (unsigned)((p.V + R - 1) / R), tc.nb, u, u_end);
+    const int nloc = p.v1 - p.v0;
+    team_range(tc.T, (unsigned)((nloc + R - 1) / R), tc.nb, u, u_end);
     float* part_s = reinterpret_cast<float*>(tc.scratch);  // [2][R][8]
     // this thread's chunks of x (k = 8 * (ttid + 256 i)) stay in registers for the whole op
     float xr[4][8];
@@ -1022,7 +1061,7 @@ __device__ void run_lm_head(const MegaParams& p, ConsRing& ring, const TeamCtx& 
     int buf = 0;
 #pragma unroll 1
     for (; u < u_end; ++u) {
-        const int nrows = min(R, p.V - u * R);
+        const int nrows = min(R, nloc - u * R);
         const uint32_t st = cons_wait(ring);
         float* ps = part_s + buf * (R * kTeamWarps);
 #pragma unroll 1
@@ -1051,7 +1090,8 @@ __device__ void run_lm_head(const MegaParams& p, ConsRing& ring, const TeamCtx& 
             float a = 0.f;
 #pragma unroll
             for (int w = 0; w < kTeamWarps; ++w) a += ps[tc.ttid * kTeamWarps + w];
-            p.logits[(size_t)u * R + tc.ttid] = __float2half_rn(a);
+            const __half lg = __float2half_rn(a);
+            for (int q = 0; q < p.tp_size; ++q) p.logits_peer[q][(size_t)p.v0 + (size_t)u * R + tc.ttid] = lg;  // every rank holds all logits
         }
         buf ^= 1;
     }
@@ -1131,6 +1171,15 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p.bar + 1) : "memory");
         gen = v;
     }
+    unsigned long long xgen = 0;  // the same for the cross-GPU barrier (tensor parallelism)
+    if (p.tp_size > 1) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(xgen) : "l"(p.xbar_peer[p.tp_rank] + 32 * kMaxTP) : "memory");
+    // after the o_proj, down_proj and lm_head operations every rank needs every rank's contributions
+    auto sync_all_ranks = [&]() {
+        if (p.tp_size > 1)
+            tp_barrier(p, xgen);
+        else
+            grid_barrier(p.bar, gen);
+    };
 
     // this step's RoPE angles (quant/fused_attn.py:43,91): freq_i = exp(i * inv_base) * pos
     if (blockIdx.x == 0 && tid < 64) {
@@ -1156,7 +1205,7 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         zero_slice(p.acc_u, p.I);
         {
             OPTRACE_BEGIN(ring);
-            run_matvec<1, X_FULL>(p, ring, tc, L.qkv.gs_steps, p.H, 3 * p.H, p.acc_qkv, nullptr, xs, xsum);
+            run_matvec<1, X_FULL>(p, ring, tc, L.qkv.gs_steps, p.H, 3 * p.Hq, p.acc_qkv, nullptr, xs, xsum);
             OPTRACE_END(ring, l, 0);
         }
         MTRACE(l * 12 + 2);
@@ -1173,14 +1222,14 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         grid_barrier(p.bar, gen);
         MTRACE(l * 12 + 5);
         // ---- O ----
-        zero_slice(p.acc_qkv, 3 * p.H);
+        zero_slice(p.acc_qkv, 3 * p.Hq);
         {
             OPTRACE_BEGIN(ring);
-            run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.H, p.H, p.acc_o, nullptr, xs, xsum, L.o_perm);
+            run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.Hq, p.H, p.acc_o, nullptr, xs, xsum, L.o_perm, p.acc_o_peer);
             OPTRACE_END(ring, l, 2);
         }
         MTRACE(l * 12 + 6);
-        grid_barrier(p.bar, gen);
+        sync_all_ranks();
         MTRACE(l * 12 + 7);
         // ---- G ----
         stage_norm<ACT, false>(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, xsum, tmp, red_s, L.mlp_perm);
@@ -1198,11 +1247,11 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         MTRACE(l * 12 + 10);
         {
             OPTRACE_BEGIN(ring);
-            run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.acc_d, nullptr, xs, xsum);
+            run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.acc_d, nullptr, xs, xsum, nullptr, p.acc_d_peer);
             OPTRACE_END(ring, l, 4);
         }
         MTRACE(l * 12 + 11);
-        grid_barrier(p.bar, gen);
+        sync_all_ranks();
         resid_src = p.resid[cur];
         resid_acc = p.acc_d;
     }
@@ -1211,10 +1260,13 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     zero_slice(p.acc_g, p.I);
     zero_slice(p.acc_u, p.I);
     run_lm_head(p, ring, tc, xs);
-    grid_barrier(p.bar, gen);
+    sync_all_ranks();
     zero_slice(p.acc_d, p.H);
     if (blockIdx.x == 0) {
-        if (tid == 0) p.bar[1] = gen;  // every CTA has arrived at the last barrier: the counter rests at this value until the next launch
+        if (tid == 0) {  // every CTA has arrived at the last barrier: the counters rest at these values until the next launch
+            p.bar[1] = gen;
+            if (p.tp_size > 1) p.xbar_peer[p.tp_rank][32 * kMaxTP] = xgen;
+        }
         if (p.next_token != nullptr) {  // greedy argmax (lowest index wins ties)
             float best = -INFINITY;
             int idx = 0x7fffffff;
@@ -1295,7 +1347,8 @@ bool mega_plan(const gptq_llama_model& m, int sms, size_t smem_max, size_t smem_
     if ((size_t)2 * pl.lm_rows * kTeamWarps * 4 > (size_t)kTeamScratch) return false;
     // per-team k-segments of o_proj / down_proj are staged in half of the xs buffer, their step sums in half of xsum
     const long long nteams = (long long)sms * kTeams;
-    const long long seg_o = ((long long)(H / kSlabCols) * (H / 32) + nteams - 1) / nteams + 1;
+    const int Hq = m.n_heads * m.head_dim;  // attention width of this rank (= H on a single GPU)
+    const long long seg_o = ((long long)(H / kSlabCols) * (Hq / 32) + nteams - 1) / nteams + 1;
     const long long seg_d = ((long long)(H / kSlabCols) * (I / 32) + nteams - 1) / nteams + 1;
     const long long seg = max(seg_o, seg_d);
     if (seg * 32 > H / 2 || seg > H / 64) return false;
@@ -1313,6 +1366,16 @@ bool mega_plan(const gptq_llama_model& m, int sms, size_t smem_max, size_t smem_
 bool mega_supported(const gptq_llama_model& m, const gptq_llama_state& st) {
     if (st.batch != 1 || m.n_layers > kMaxLayers || m.head_dim != kHD) return false;
     if (m.hidden % kSlabCols || m.intermediate % kSlabCols || m.hidden > 8192 || m.intermediate > 32768 || m.hidden % 64) return false;
+    if ((3 * m.n_heads * m.head_dim) % kSlabCols) return false;  // the (local) fused qkv width is dealt in 256-column slabs
+    if (st.tp != nullptr) {
+        const gptq_llama_tp& tp = *st.tp;
+        if (tp.size < 1 || tp.size > kMaxTP || tp.rank < 0 || tp.rank >= tp.size) return false;
+        if (tp.vocab_begin < 0 || tp.vocab_end > m.vocab || tp.vocab_begin >= tp.vocab_end) return false;
+        for (int q = 0; q < tp.size; ++q)
+            if (q != tp.rank && (tp.peer_scratch[q] == nullptr || tp.peer_logits[q] == nullptr)) return false;
+    } else if (m.n_heads * m.head_dim != m.hidden) {
+        return false;
+    }
     for (int l = 0; l < m.n_layers; ++l) {
         const gptq_llama_layer& ly = m.layers[l];
         const gptq_qweight* ws[5] = {&ly.qkv, &ly.o, &ly.gate, &ly.up, &ly.down};
@@ -1331,7 +1394,7 @@ size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq) {
     (void)max_seq;
     const size_t max_teams = 1024;  // >= kTeams * SM count of any device this library runs on
     return al256((size_t)m.hidden * 2) * 2 + al256((size_t)3 * m.hidden * 4) + al256((size_t)m.hidden * 4) * 2 + al256((size_t)m.intermediate * 4) * 2 +
-           al256(max_teams * kRec * 4) + al256(128 * 4) + 256;
+           al256(max_teams * kRec * 4) + al256(128 * 4) + 256 + (kMaxTP + 1) * 256;
 }
 
 cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream) {
@@ -1349,7 +1412,9 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     if (sms * kTeams > 1024 || !mega_plan(m, sms, (size_t)smem_optin, fa.sharedSizeBytes, pl)) return cudaErrorInvalidConfiguration;
 
     MegaParams p{};
-    p.n_layers = m.n_layers; p.H = m.hidden; p.I = m.intermediate; p.V = m.vocab; p.n_heads = m.n_heads;
+    p.n_layers = m.n_layers; p.H = m.hidden; p.Hq = m.n_heads * m.head_dim; p.I = m.intermediate; p.V = m.vocab; p.n_heads = m.n_heads;
+    p.v0 = st.tp != nullptr ? st.tp->vocab_begin : 0;
+    p.v1 = st.tp != nullptr ? st.tp->vocab_end : m.vocab;
     p.max_seq = st.max_seq;
     p.n_stages = pl.n_stages;
     p.lm_rows = pl.lm_rows;
@@ -1372,11 +1437,24 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
         off += al256(bytes);
         return q;
     };
+    // the head of the region has the same layout on every tensor-parallel rank (it depends on the hidden size only): peers address
+    // acc_o / acc_d / xbar of this rank through its scratch base
     p.resid[0] = reinterpret_cast<__half*>(take((size_t)m.hidden * 2));
     p.resid[1] = reinterpret_cast<__half*>(take((size_t)m.hidden * 2));
-    p.acc_qkv = reinterpret_cast<float*>(take((size_t)3 * m.hidden * 4));
     p.acc_o = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
     p.acc_d = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
+    unsigned long long* xbar = reinterpret_cast<unsigned long long*>(take((kMaxTP + 1) * 256));
+    const gptq_llama_tp* tp = st.tp;
+    p.tp_size = tp != nullptr ? tp->size : 1;
+    p.tp_rank = tp != nullptr ? tp->rank : 0;
+    for (int q = 0; q < p.tp_size; ++q) {
+        uint8_t* base = (tp != nullptr && q != tp->rank) ? reinterpret_cast<uint8_t*>(tp->peer_scratch[q]) : scratch;
+        p.acc_o_peer[q] = reinterpret_cast<float*>(base + (reinterpret_cast<uint8_t*>(p.acc_o) - scratch));
+        p.acc_d_peer[q] = reinterpret_cast<float*>(base + (reinterpret_cast<uint8_t*>(p.acc_d) - scratch));
+        p.xbar_peer[q] = reinterpret_cast<unsigned long long*>(base + (reinterpret_cast<uint8_t*>(xbar) - scratch));
+        p.logits_peer[q] = reinterpret_cast<__half*>((tp != nullptr && q != tp->rank) ? tp->peer_logits[q] : st.logits);
+    }
+    p.acc_qkv = reinterpret_cast<float*>(take((size_t)3 * p.Hq * 4));
     p.acc_g = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
     p.acc_u = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
     p.part = reinterpret_cast<float*>(take((size_t)1024 * kRec * 4));
@@ -1384,7 +1462,7 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     p.bar = reinterpret_cast<unsigned long long*>(take(256));
     // One tensor map per row stride serves every layer: class 0 = qkv (N = 3H), 1 = o and down (N = H), 2 = gate and up (N = I).
     // Its base is the lowest qweight address of the class; a matrix is addressed through the chunk coordinate (128-byte units).
-    const int classN[3] = {3 * m.hidden, m.hidden, m.intermediate};
+    const int classN[3] = {3 * m.n_heads * m.head_dim, m.hidden, m.intermediate};
     uintptr_t base[3] = {UINTPTR_MAX, UINTPTR_MAX, UINTPTR_MAX}, top[3] = {0, 0, 0};
     int rows_max[3] = {0, 0, 0};
     auto visit = [&](const gptq_qweight& w, int c) {

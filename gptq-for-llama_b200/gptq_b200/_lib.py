@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('GPTQ_B200_LIB') or os.path.join(os.path.dirname(_HERE), 'libgptq_b200.so')  # env override: A/B builds during development
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_void_p, c_int, c_int64, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
 
@@ -45,10 +45,18 @@ class LlamaModel(ctypes.Structure):
                 ('rope_base', c_float), ('layers', ctypes.POINTER(LlamaLayer)), ('embed', c_void_p), ('final_norm', c_void_p), ('lm_head', c_void_p)]
 
 
+MAX_TP = 8
+
+
+class LlamaTP(ctypes.Structure):
+    """struct gptq_llama_tp."""
+    _fields_ = [('size', c_int), ('rank', c_int), ('vocab_begin', c_int), ('vocab_end', c_int), ('peer_scratch', c_void_p * MAX_TP), ('peer_logits', c_void_p * MAX_TP)]
+
+
 class LlamaState(ctypes.Structure):
     """struct gptq_llama_state."""
     _fields_ = [('batch', c_int), ('max_seq', c_int), ('k_cache', c_void_p), ('v_cache', c_void_p), ('tokens', c_void_p), ('positions', c_void_p),
-                ('logits', c_void_p), ('next_tokens', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_size_t)]
+                ('logits', c_void_p), ('next_tokens', c_void_p), ('scratch', c_void_p), ('scratch_bytes', c_size_t), ('tp', ctypes.POINTER(LlamaTP))]
 
 
 # name -> (restype, argtypes); must list every symbol include/gptq_b200.h declares
@@ -71,6 +79,10 @@ SIGNATURES = {
     'gptq_llama_decode_step': (c_int, [ctypes.POINTER(LlamaModel), ctypes.POINTER(LlamaState), c_void_p]),
     'gptq_llama_decode_launches': (c_int, [ctypes.POINTER(LlamaModel), ctypes.POINTER(LlamaState)]),
     'gptq_llama_persistent_scratch_offset': (c_size_t, [ctypes.POINTER(LlamaModel), c_int, c_int]),
+    'gptq_ipc_alloc': (c_int, [c_size_t, ctypes.POINTER(c_void_p), ctypes.c_char_p]),
+    'gptq_ipc_open': (c_int, [ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    'gptq_ipc_close': (c_int, [c_void_p]),
+    'gptq_ipc_free': (c_int, [c_void_p]),
 }
 
 # gptq_status (include/gptq_b200.h)

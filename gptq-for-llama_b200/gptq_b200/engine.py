@@ -12,7 +12,7 @@ import math
 import torch
 
 from . import ops
-from ._lib import LlamaLayer, LlamaModel, LlamaState, QWeight, check, lib
+from ._lib import LlamaLayer, LlamaModel, LlamaState, LlamaTP, QWeight, check, lib
 
 c_void_p, c_int, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
 
@@ -24,6 +24,7 @@ LLAMA_SHAPES = {  # hidden, intermediate, layers, heads
     '65b': (8192, 22016, 80, 64),
     'tiny': (256, 704, 2, 2),    # intermediate not a multiple of 256: exercises the kernel-chain engine
     'tiny256': (256, 768, 2, 2),  # eligible for the persistent single-kernel path
+    'tiny512': (512, 1024, 2, 4),  # shardable over 2 tensor-parallel ranks (2 heads and 2 slabs of 256 MLP columns each)
 }
 
 
@@ -49,6 +50,20 @@ class QLayerWeights:
         zeros = ops.unpack_qzeros(self.qzeros, self.bits).index_select(1, perm)
         return QLayerWeights(self.qweight.index_select(1, perm), self.scales.index_select(1, perm), ops.pack_qzeros(zeros, self.bits), self.g_idx, self.bits,
                              self.groupsize)
+
+    def column_slice(self, cols):
+        """The layer restricted to output columns `cols` (a LongTensor of whole groups of 8 consecutive columns): out[:, j] = full[:, cols[j]]."""
+        ipb = 32 // self.bits
+        assert cols.numel() % ipb == 0 and bool((cols.view(-1, ipb)[:, 0] % ipb == 0).all()), 'column shards must keep the packed zero words whole'
+        zcols = (cols.view(-1, ipb)[:, 0] // ipb).contiguous()
+        return QLayerWeights(self.qweight.index_select(1, cols), self.scales.index_select(1, cols), self.qzeros.index_select(1, zcols), self.g_idx, self.bits, self.groupsize)
+
+    def row_slice(self, k0, k1):
+        """The layer restricted to input features [k0, k1) (whole quantisation groups, no act-order): a K-shard whose partial outputs add up."""
+        assert self.hint == self.groupsize and k0 % self.groupsize == 0 and k1 % self.groupsize == 0 and self.bits in (2, 4, 8)
+        ipb, gs = 32 // self.bits, self.groupsize
+        g = (torch.arange(k1 - k0, device=self.qweight.device) // gs).to(torch.int32)
+        return QLayerWeights(self.qweight[k0 // ipb:k1 // ipb], self.scales[k0 // gs:k1 // gs], self.qzeros[k0 // gs:k1 // gs], g, self.bits, gs)
 
     @classmethod
     def from_module(cls, m):
@@ -105,8 +120,14 @@ def kernel_layers(layers, allow_perm=True):
 class LlamaDecoder:
     """Owns the weights, the KV cache and the captured graph; `step()` decodes one token per sequence."""
 
-    def __init__(self, layers, embed, final_norm, lm_head, n_heads, rms_eps=1e-6, rope_base=10000.0, batch=1, max_seq=2048, use_graph=True):
+    def __init__(self, layers, embed, final_norm, lm_head, n_heads, rms_eps=1e-6, rope_base=10000.0, batch=1, max_seq=2048, use_graph=True, head_dim=None,
+                 tp=None):
+        """tp = (rank, size, vocab_begin, vocab_end): this process holds one tensor-parallel shard (see shard_for_rank / gptq_llama_tp): `layers`,
+        `lm_head` and `n_heads` are the LOCAL ones, head_dim must be given, and torch.distributed must be initialised (the scratch and logits
+        buffers of the ranks are exchanged as CUDA IPC handles)."""
         self.dev = embed.device
+        self.tp = tp
+        self.head_dim = head_dim or embed.shape[1] // n_heads
         self.layers = layers  # list of dicts: qkv, o, gate, up, down (QLayerWeights), input_norm, post_norm (fp16 tensors)
         self.embed, self.final_norm, self.lm_head = embed.contiguous(), final_norm.contiguous(), lm_head.contiguous()
         self.hidden = embed.shape[1]
@@ -123,28 +144,34 @@ class LlamaDecoder:
             self._layer_arr = (LlamaLayer * len(layers))()
             self._fill_layer_structs()
             m = LlamaModel()
-            m.n_layers, m.hidden, m.n_heads, m.head_dim = len(layers), self.hidden, n_heads, self.hidden // n_heads
+            m.n_layers, m.hidden, m.n_heads, m.head_dim = len(layers), self.hidden, n_heads, self.head_dim
             m.intermediate, m.vocab, m.rms_eps, m.rope_base = self.intermediate, self.vocab, rms_eps, rope_base
             m.layers = ctypes.cast(self._layer_arr, ctypes.POINTER(LlamaLayer))
             m.embed, m.final_norm, m.lm_head = self.embed.data_ptr(), self.final_norm.data_ptr(), self.lm_head.data_ptr()
             self.model = m
-            cache_shape = (len(layers), batch, n_heads, max_seq, self.hidden // n_heads)
+            cache_shape = (len(layers), batch, n_heads, max_seq, self.head_dim)
             self.k_cache = torch.zeros(cache_shape, dtype=torch.float16, device=self.dev)
             self.v_cache = torch.zeros(cache_shape, dtype=torch.float16, device=self.dev)
             self.tokens = torch.zeros(batch, dtype=torch.int32, device=self.dev)
             self.positions = torch.zeros(batch, dtype=torch.int32, device=self.dev)
-            self.logits = torch.zeros(batch, self.vocab, dtype=torch.float16, device=self.dev)
             self.next_tokens = torch.zeros(batch, dtype=torch.int32, device=self.dev)
             nbytes = lib.gptq_llama_scratch_bytes(ctypes.byref(m), batch, max_seq)
             if nbytes == 0:
                 raise ValueError('unsupported decode configuration (batch must be 1..8)')
-            self.scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+            self._tp_struct = None
+            if tp is None:
+                self.logits = torch.zeros(batch, self.vocab, dtype=torch.float16, device=self.dev)
+                self.scratch = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+            else:
+                self._setup_tp(nbytes)
             st = LlamaState()
             st.batch, st.max_seq = batch, max_seq
             st.k_cache, st.v_cache = self.k_cache.data_ptr(), self.v_cache.data_ptr()
             st.tokens, st.positions = self.tokens.data_ptr(), self.positions.data_ptr()
             st.logits, st.next_tokens = self.logits.data_ptr(), self.next_tokens.data_ptr()
             st.scratch, st.scratch_bytes = self.scratch.data_ptr(), nbytes
+            if self._tp_struct is not None:
+                st.tp = ctypes.pointer(self._tp_struct)
             self.state = st
             if any(p is not None for pm in self.perms for p in pm.values()) and self.launches_per_step() != 1:
                 # the input gathers exist only in the persistent kernel: act-order layers go back to their stored form
@@ -155,6 +182,42 @@ class LlamaDecoder:
         self._stream = torch.cuda.Stream(self.dev)
         if use_graph:
             self._capture()
+
+    def _setup_tp(self, scratch_bytes):
+        """Scratch and logits in IPC-shareable device memory; every rank maps every other rank's buffers (gptq_llama_tp)."""
+        import torch.distributed as dist
+        rank, size, v0, v1 = self.tp
+        assert self.batch == 1 and dist.is_initialized() and dist.get_world_size() == size
+
+        def ipc_buffer(nbytes, dtype):
+            ptr, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            check(lib.gptq_ipc_alloc(nbytes, ctypes.byref(ptr), handle))
+
+            class _Raw:  # zero-copy torch view of the raw allocation
+                __cuda_array_interface__ = {'shape': (nbytes, ), 'typestr': '|u1', 'data': (ptr.value, False), 'version': 2}
+
+            t = torch.as_tensor(_Raw(), device=self.dev)
+            return ptr.value, handle.raw, t.view(dtype)
+
+        self._scratch_ptr, h_scr, self.scratch = ipc_buffer(scratch_bytes, torch.uint8)
+        self._logits_ptr, h_log, logits = ipc_buffer(self.batch * self.vocab * 2, torch.float16)
+        self.logits = logits.view(self.batch, self.vocab)
+        handles = [None] * size
+        dist.all_gather_object(handles, (h_scr, h_log))
+        t = LlamaTP()
+        t.size, t.rank, t.vocab_begin, t.vocab_end = size, rank, v0, v1
+        self._peer_maps = []
+        for q, (hs, hl) in enumerate(handles):
+            if q == rank:
+                t.peer_scratch[q], t.peer_logits[q] = self._scratch_ptr, self._logits_ptr
+                continue
+            for field, h in ((t.peer_scratch, hs), (t.peer_logits, hl)):
+                ptr = ctypes.c_void_p()
+                check(lib.gptq_ipc_open(h, ctypes.byref(ptr)))
+                field[q] = ptr.value
+                self._peer_maps.append(ptr.value)
+        self._tp_struct = t
+        dist.barrier()  # every rank has mapped every buffer before anybody launches
 
     def _fill_layer_structs(self):
         for i, ly in enumerate(self.klayers):
@@ -261,6 +324,57 @@ def synthetic_llama(size='7b', bits=4, groupsize=128, act_order=False, vocab=320
     lm_head = (torch.randn(vocab, hidden, device=dev, generator=gen) * 0.02).half()
     final_norm = (torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half()
     return LlamaDecoder(L, embed, final_norm, lm_head, heads, **kw)
+
+
+def shard_for_rank(layers, lm_head, n_heads, head_dim, rank, size):
+    """Tensor-parallel shard of a layer stack (BASELINE config 5): qkv columns of this rank's heads (q | k | v), o_proj rows
+    of the same heads, gate/up column slabs of 256 with the matching down_proj rows, lm_head rows.  Plain g_idx only (row shards keep whole groups).
+    Returns (local layers, local lm_head, local heads, (vocab_begin, vocab_end))."""
+    assert n_heads % size == 0, 'heads must divide over the ranks'
+    hl = n_heads // size
+    H = n_heads * head_dim
+    dev = lm_head.device
+    hcols = torch.arange(rank * hl * head_dim, (rank + 1) * hl * head_dim, device=dev)
+    out = []
+    for ly in layers:
+        inter = ly['gate'].qweight.shape[1]
+        nslab = inter // 256
+        c0, c1 = rank * nslab // size * 256, (rank + 1) * nslab // size * 256
+        mcols = torch.arange(c0, c1, device=dev)
+        out.append(dict(qkv=ly['qkv'].column_slice(torch.cat([hcols, H + hcols, 2 * H + hcols])), o=ly['o'].row_slice(int(hcols[0]), int(hcols[-1]) + 1),
+                        gate=ly['gate'].column_slice(mcols), up=ly['up'].column_slice(mcols), down=ly['down'].row_slice(c0, c1), input_norm=ly['input_norm'],
+                        post_norm=ly['post_norm']))
+    V = lm_head.shape[0]
+    v0, v1 = rank * V // size, (rank + 1) * V // size
+    return out, lm_head[v0:v1].contiguous(), hl, (v0, v1)
+
+
+def synthetic_llama_tp(size_name, rank, world, bits=4, groupsize=128, vocab=32000, device='cuda:0', seed=0, n_layers=None, full=None, **kw):
+    """One tensor-parallel rank of the random-init model `synthetic_llama(size_name, seed=seed)` (every rank generates the same full model from the same
+    seed layer by layer and keeps its shard), or of the given `full` decoder's weights."""
+    hidden, inter, layers, heads = LLAMA_SHAPES[size_name]
+    layers = n_layers or layers
+    dev = torch.device(device)
+    hd = hidden // heads
+    if full is not None:
+        L, lm_head, hl, (v0, v1) = shard_for_rank(full.layers, full.lm_head, heads, hd, rank, world)
+        return LlamaDecoder(L, full.embed, full.final_norm, lm_head, hl, head_dim=hd, tp=(rank, world, v0, v1), **kw)
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    L = []
+    fake_head = torch.empty(0, hidden, device=dev)
+    for _ in range(layers):  # shard as we go: a 65B model never exists whole on one GPU
+        gate = random_qlayer(hidden, inter, bits, groupsize, dev, gen)
+        up = random_qlayer(hidden, inter, bits, groupsize, dev, gen)
+        ly = dict(qkv=random_qlayer(hidden, 3 * hidden, bits, groupsize, dev, gen), o=random_qlayer(hidden, hidden, bits, groupsize, dev, gen), gate=gate, up=up,
+                  down=random_qlayer(inter, hidden, bits, groupsize, dev, gen), input_norm=(torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half(),
+                  post_norm=(torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half())
+        L.append(shard_for_rank([ly], fake_head, heads, hd, rank, world)[0][0])
+        del ly, gate, up
+    embed = (torch.randn(vocab, hidden, device=dev, generator=gen) * 0.5).half()
+    lm_head = (torch.randn(vocab, hidden, device=dev, generator=gen) * 0.02).half()
+    final_norm = (torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half()
+    v0, v1 = rank * vocab // world, (rank + 1) * vocab // world
+    return LlamaDecoder(L, embed, final_norm, lm_head[v0:v1].contiguous(), heads // world, head_dim=hd, tp=(rank, world, v0, v1), **kw)
 
 
 def from_hf_quant_model(model, batch=1, max_seq=2048, **kw):

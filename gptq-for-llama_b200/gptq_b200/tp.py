@@ -3,8 +3,10 @@
 The reference has no tensor parallelism (its "multi-GPU" is layer placement, llama.py:328-382); this is new
 design on top of the packed layout, checked against the single-GPU result:
 
-* column parallel (fused qkv, gate, up): slice N.  qweight[:, n0:n1], scales[:, n0:n1], qzeros[:, n0*bits/32 : n1*bits/32];
+* column parallel (gate, up; q, k, v SEPARATELY): slice N.  qweight[:, n0:n1], scales[:, n0:n1], qzeros[:, n0*bits/32 : n1*bits/32];
   g_idx is replicated.  Shard boundaries are multiples of 32 columns.  No communication (attention is head-local).
+  A FUSED qkv layer is [q | k | v] along N: a contiguous slice of it is not a set of heads; shard it per head with
+  ``engine.shard_for_rank`` (what the tensor-parallel decode engine does), or shard q, k, v before fusing them.
 * row parallel (o_proj, down_proj): slice K at GROUP boundaries so that every shard keeps the trivial
   ``k // groupsize`` map (and therefore the tuned kernels): 65B down_proj has K = 22016 = 172 groups, i.e. 21.5
   per rank, so shards are uneven by one group.  Each rank multiplies its slice of x; one all-reduce (sum) of the

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define GPTQ_B200_ABI_VERSION 3 /* 2: gptq_llama_layer gained the act-order input gathers; 3: gptq_llama_persistent_scratch_offset */
+#define GPTQ_B200_ABI_VERSION 4 /* 2: act-order input gathers; 3: gptq_llama_persistent_scratch_offset; 4: tensor parallelism (gptq_llama_tp, gptq_ipc_*) */
 
 typedef void* gptq_stream_t; /* cudaStream_t */
 
@@ -148,6 +148,23 @@ typedef struct gptq_llama_model {
     const void* lm_head;    /* fp16 [vocab, hidden] (never quantized, llama_inference.py:46-48) */
 } gptq_llama_model;
 
+#define GPTQ_MAX_TP 8
+
+/* Tensor-parallel decode (BASELINE config 5: LLaMA-65B across 8 GPUs; the reference has no equivalent, its multi-GPU mode is layer
+ * placement, llama.py:328-382).  One process per GPU; every rank passes ITS shard of every layer in gptq_llama_model:
+ *   qkv   columns of this rank's heads (q | k | v of those heads, N = 3 * n_heads * head_dim), o rows of the same heads (K = n_heads * head_dim),
+ *   gate/up column slices (N = intermediate), down the matching row slice (K = intermediate), with model->n_heads / ->intermediate the LOCAL
+ *   counts and model->hidden / ->vocab the full ones; lm_head points to this rank's rows [vocab_begin, vocab_end).
+ * The persistent kernel adds the o_proj / down_proj partial sums into every rank's accumulators over NVLink (peer stores), so there is no
+ * separate all-reduce; peer_scratch / peer_logits are the scratch and logits buffers of ALL ranks mapped into this process (gptq_ipc_*),
+ * [rank] being the own ones.  Every rank must call gptq_llama_decode_step for the same step; the call still returns asynchronously. */
+typedef struct gptq_llama_tp {
+    int size, rank;
+    int vocab_begin, vocab_end;
+    void* peer_scratch[GPTQ_MAX_TP];
+    void* peer_logits[GPTQ_MAX_TP];
+} gptq_llama_tp;
+
 typedef struct gptq_llama_state {
     int batch;   /* sequences decoded in lock-step, 1..8 */
     int max_seq; /* KV-cache capacity in tokens */
@@ -159,6 +176,7 @@ typedef struct gptq_llama_state {
     int32_t* next_tokens;     /* device int32 [batch] out: argmax of logits, or NULL to skip */
     void* scratch;            /* device, gptq_llama_scratch_bytes() bytes, zero-filled once */
     size_t scratch_bytes;
+    const gptq_llama_tp* tp;  /* NULL: single GPU */
 } gptq_llama_state;
 
 size_t gptq_llama_scratch_bytes(const gptq_llama_model* model, int batch, int max_seq);
@@ -170,6 +188,14 @@ int gptq_llama_decode_launches(const gptq_llama_model* model, const gptq_llama_s
  * stream ping-pong: two fp16 [hidden] vectors, each padded to 256 bytes (after a step: [0] = the residual entering the last
  * layer, [1] = the residual after the last layer's attention block). */
 size_t gptq_llama_persistent_scratch_offset(const gptq_llama_model* model, int batch, int max_seq);
+
+/* Device memory that other processes of the node can map (CUDA IPC), for the tensor-parallel scratch / logits buffers:
+ * alloc returns a zero-filled device buffer and its 64-byte handle (to be sent to the peers, e.g. with torch.distributed);
+ * open maps a peer's buffer into this process.  close / free release them. */
+int gptq_ipc_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int gptq_ipc_open(const unsigned char handle[64], void** ptr);
+int gptq_ipc_close(void* ptr);
+int gptq_ipc_free(void* ptr);
 
 #ifdef __cplusplus
 }

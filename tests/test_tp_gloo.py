@@ -85,3 +85,34 @@ def test_tp_quantlinear_world2_gloo():
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(2))
     assert res == {0: True, 1: True}
+
+
+def test_decoder_shards_reassemble():
+    """engine.shard_for_rank (the tensor-parallel decode engine's sharding, BASELINE config 5): qkv columns go per HEAD (q | k | v of the rank's
+    heads), o_proj rows follow the same heads, gate/up columns in slabs of 256 with the matching down_proj rows; every shard dequantises to exactly
+    the corresponding block of the full matrix, and the shards tile it."""
+    from gptq_b200 import engine
+    H, I, NH, hd, bits, gs = 512, 1024, 4, 128, 4, 128
+    def layer(K, N, seed):
+        qw, s, qz, g, _ = O.random_packed(K, N, bits, gs, seed=seed)
+        return engine.QLayerWeights(qw, s, qz, g, bits, gs)
+    ly = dict(qkv=layer(H, 3 * H, 1), o=layer(H, H, 2), gate=layer(H, I, 3), up=layer(H, I, 4), down=layer(I, H, 5), input_norm=torch.ones(H).half(),
+              post_norm=torch.ones(H).half())
+    lm_head = torch.randn(96, H).half()
+    deq = lambda w: O.dequant(w.qweight, w.scales, w.qzeros, w.g_idx, bits)
+    full = {k: deq(v) for k, v in ly.items() if hasattr(v, 'qweight')}
+    seen_heads, seen_cols, seen_vocab = [], [], []
+    for rank in range(2):
+        (sh, ), head, hl, (v0, v1) = engine.shard_for_rank([ly], lm_head, NH, hd, rank, 2)
+        assert hl == 2 and torch.equal(head, lm_head[v0:v1])
+        seen_vocab.append((v0, v1))
+        hc = torch.arange(rank * hl * hd, (rank + 1) * hl * hd)
+        assert torch.equal(deq(sh['qkv']), full['qkv'][:, torch.cat([hc, H + hc, 2 * H + hc])])
+        assert torch.equal(deq(sh['o']), full['o'][hc])
+        c0, c1 = rank * 2 * 256, (rank + 1) * 2 * 256
+        assert torch.equal(deq(sh['gate']), full['gate'][:, c0:c1]) and torch.equal(deq(sh['up']), full['up'][:, c0:c1])
+        assert torch.equal(deq(sh['down']), full['down'][c0:c1])
+        assert sh['o'].hint == gs and sh['down'].hint == gs  # row shards keep the plain g_idx: the tuned kernels apply
+        seen_heads.append(hc)
+        seen_cols.append((c0, c1))
+    assert torch.equal(torch.cat(seen_heads), torch.arange(H)) and seen_cols == [(0, 512), (512, 1024)] and seen_vocab == [(0, 48), (48, 96)]
