@@ -51,6 +51,7 @@ CONFIGS = {  # name -> (size, bits, act_order, BASELINE.json config)
     '7b': ('7b', 4, False, 'LLaMA-7B int4 g128 batch=1 decode'),
     '13b-int3': ('13b', 3, True, 'LLaMA-13B int3 g128 act-order batch=1 decode'),
     '65b': ('65b', 4, False, 'LLaMA-65B int4 g128 batch=1 decode on ONE GPU'),
+    '65b-tp': ('65b', 4, False, 'LLaMA-65B int4 g128 batch=1 decode, tensor-parallel over the N GPUs (BASELINE config 5)'),
 }
 GROUP = 128
 
@@ -220,7 +221,11 @@ def run_decode(args):
 
     size, bits, act, title = CONFIGS[args.config]
     steps, warm = max(1, args.steps), max(3, args.warmup)
-    dec = engine.synthetic_llama(size, bits=bits, groupsize=GROUP, act_order=act, device=str(dev), seed=rank, max_seq=SEQ)
+    tp = args.config.endswith('-tp') and world > 1  # ONE sequence sharded over the ranks (strong scaling) instead of one replica per rank
+    if tp:
+        dec = engine.synthetic_llama_tp(size, rank, world, bits=bits, groupsize=GROUP, device=str(dev), seed=0, max_seq=SEQ)
+    else:
+        dec = engine.synthetic_llama(size, bits=bits, groupsize=GROUP, act_order=act, device=str(dev), seed=rank, max_seq=SEQ)
     # synthetic context: the cache holds seq-1 = 2047 tokens of random K/V; the step decodes token 2048
     dec.k_cache.normal_(0, 0.5)
     dec.v_cache.normal_(0, 0.5)
@@ -286,23 +291,25 @@ def run_decode(args):
     t_dev, t_e2e = tt.tolist()
     if rank == 0:
         base, _ = cpu_baseline(2, 1) if (world == 1 and args.config == '7b') else (None, None)
-        H, I, V, L = dec.hidden, dec.intermediate, dec.vocab, len(dec.layers)
+        H, I, V, L = dec.hidden, engine.LLAMA_SHAPES[size][1], dec.vocab, len(dec.layers)
+        jobs = 1 if tp else world  # sequences decoded concurrently
         # algorithmic bytes per token: quant linears of the CHECKPOINT (not of derived buffers) + fp16 lm_head + KV cache read at this context
         per_layer = alg_bytes_qlinear(H, 3 * H, bits) + alg_bytes_qlinear(H, H, bits) + 2 * alg_bytes_qlinear(H, I, bits) + alg_bytes_qlinear(I, H, bits)
         kv = 2 * L * SEQ * H * 2
         step_bytes = L * per_layer + V * H * 2 + kv
         t_step = t_dev / steps
         line = {
-            'metric': METRIC if args.config == '7b' else f'tokens/sec {title}', 'value': world * steps / t_dev, 'unit': 'tokens/s', 'n_gpus': world, 'steps': steps,
-            'warmup': warm, 'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
+            'metric': METRIC if args.config == '7b' else f'tokens/sec {title}', 'value': jobs * steps / t_dev, 'unit': 'tokens/s', 'n_gpus': world, 'steps': steps,
+            'warmup': warm, 'ms_per_step': t_step * 1e3, 'higher_is_better': True, 'scaling': 'strong' if tp else 'weak', 'vs_baseline': None, 'dtype': 'f16', 'data': 'synthetic',
             'config': {
                 'workload': f'{title}, context {pos} (seq={SEQ}), {L} layers, random-init packed weights',
-                'parallelism': 'replicas only (one independent sequence per GPU, no data-path collective)' if world > 1 else 'single GPU',
+                'parallelism': (f'tp{world}: heads / MLP columns sharded, o_proj and down_proj partial sums RED-added into every rank over NVLink inside the kernel' if tp else
+                                'replicas only (one independent sequence per GPU, no data-path collective)' if world > 1 else 'single GPU'),
                 'l2': f'each step streams {L * per_layer / 1e9:.1f} GB of weights + {kv / 1e9:.2f} GB of KV cache (inputs >> 126 MB L2); no explicit flush needed',
                 'arithmetic': 'raw int4 nibbles x fp16 activations on the tensor pipe (mma.sync, exact products, fp32 accumulate), fp16 scale and zero applied once per '
                               'quantisation group on the fp32 accumulator, fp16 store; within 1e-3 of the reference kernel (tests/)',
             },
-            'e2e': {'value': world * steps / t_e2e, 'unit': 'tokens/s', 'h2d_bytes_per_step': 8, 'd2h_bytes_per_step': dec.vocab * 2,
+            'e2e': {'value': jobs * steps / t_e2e, 'unit': 'tokens/s', 'h2d_bytes_per_step': 8, 'd2h_bytes_per_step': dec.vocab * 2,
                     'note': 'host token+position (pinned) -> H2D -> CUDA-graph decode step -> D2H fp16 logits, synchronised every step'},
             'gpu_launches': dec.launches_per_step() * steps,
             'roofline': None,
@@ -311,7 +318,8 @@ def run_decode(args):
         assert dec.launches_per_step() == 1, 'the persistent kernel must be the measured path'
         # the whole token is ONE persistent kernel: its launch duration is the step time measured above with CUDA events
         line['roofline'] = {'bound': 'hbm', 'kernel': 'llama_decode_mega_kernel (persistent decode step: all quantized matvecs + attention + lm_head of a token)',
-                            'achieved': step_bytes / t_step / 1e9, 'peak': peak, 'unit': 'GB/s', 'frac': step_bytes / t_step / 1e9 / peak, 'peak_source': peak_src,
+                            'achieved': step_bytes / t_step / 1e9 / (world if tp else 1), 'peak': peak, 'unit': 'GB/s',
+                            'frac': step_bytes / t_step / 1e9 / peak / (world if tp else 1), 'peak_source': peak_src + (' per GPU' if tp else ''),
                             'bytes_per_launch': step_bytes, 'us_per_launch': t_step * 1e6, 'frac_of_8TBs': step_bytes / t_step / 8e12,
                             'traffic': NCU_TRAFFIC_BYTES.get(args.config), 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/'}
         if mlp is None and bits == 4 and not act:

@@ -406,22 +406,25 @@ __device__ __forceinline__ void grid_barrier(unsigned long long* bar, unsigned l
     cta_sync();
 }
 
-// Cross-GPU barrier of all CTAs of all tensor-parallel ranks: every CTA adds 1 to ITS source line of every rank's counter block
-// (system-scope release after a system fence, so its remote REDs are visible first) and polls its own rank's lines.
+// Cross-GPU barrier of all CTAs of all tensor-parallel ranks: every CTA adds 1 to ITS source line of every rank's counter block and polls its
+// own rank's lines.  ONE system-scope fence per CTA makes its remote REDs (partial sums in the peers' accumulators) visible before its
+// arrivals; the arrivals themselves and the polls are relaxed (the counters and the data they guard live in the polling GPU's own L2, and
+// everything that is read afterwards bypasses L1).
 __device__ __forceinline__ void tp_barrier(const MegaParams& p, unsigned long long& target) {
     cta_sync();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         asm volatile("fence.acq_rel.sys;" ::: "memory");
         for (int q = 0; q < p.tp_size; ++q)
-            asm volatile("red.release.sys.global.add.u64 [%0], 1;" ::"l"(p.xbar_peer[q] + 32 * p.tp_rank) : "memory");
+            asm volatile("red.relaxed.sys.global.add.u64 [%0], 1;" ::"l"(p.xbar_peer[q] + 32 * p.tp_rank) : "memory");
         const unsigned long long* mine = p.xbar_peer[p.tp_rank];
         for (int q = 0; q < p.tp_size; ++q) {
             unsigned long long v;
             do {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + 32 * q) : "memory");
+                asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine + 32 * q) : "memory");
             } while (v < target);
         }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     cta_sync();
 }
