@@ -38,15 +38,14 @@ if '--impl' in sys.argv and 'reference' in sys.argv:
     # the CPU arm uses every host core it may run on; torchrun exports OMP_NUM_THREADS=1, which must not leak into it.
     # (set before torch / libgomp are loaded)
     os.environ['OMP_NUM_THREADS'] = os.environ.get('BENCH_CPU_THREADS', str(_host_threads()))
-    os.environ.setdefault('OMP_PROC_BIND', 'spread')
 
 import torch  # noqa: E402
 
 METRIC = 'tokens/sec LLaMA-7B int4 g128 batch=1; matvec HBM GB/s vs 8 TB/s roofline'
 SEQ = 2048
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of llama_decode_mega_kernel on the 32-layer model at context 2047
-# (ncu --set full, profiles/r2_mega_summary.txt)
-NCU_TRAFFIC_BYTES = {'7b': None}
+# (ncu --set full, profiles/r2_mega_summary.txt, profiles/r2_mega_final.ncu-rep)
+NCU_TRAFFIC_BYTES = {'7b': 4737481728}  # 4.7074 GB read + 30.1 MB written (algorithmic: 4.7084 GB)
 CONFIGS = {  # name -> (size, bits, act_order, BASELINE.json config)
     '7b': ('7b', 4, False, 'LLaMA-7B int4 g128 batch=1 decode'),
     '13b-int3': ('13b', 3, True, 'LLaMA-13B int3 g128 act-order batch=1 decode'),

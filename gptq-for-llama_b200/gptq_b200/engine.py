@@ -278,8 +278,35 @@ class LlamaDecoder:
         self.positions.fill_(int(position))
 
     @torch.no_grad()
-    def generate(self, prompt_ids, max_new_tokens):
-        """Greedy decode (batch 1): the prompt is fed token by token through the same decode step."""
+    def prefill(self, prompt_ids):
+        """Batched pass over the first len(prompt) - 1 prompt tokens that fills the static KV cache (batch 1): per layer the quantized linears on
+        the tcgen05 GEMM path (gptq_qlinear_fwd / gptq_fused_mlp_fwd with M = tokens), the RoPE and RMSNorm kernels, torch SDPA for the causal
+        attention (as the reference's QuantLlamaAttention does, quant/fused_attn.py:154-155); keys are cached after RoPE.  The LAST prompt token then
+        goes through the decode step like every generated one (it produces the first logits).  Returns the number of cached positions."""
+        assert self.batch == 1 and self.tp is None
+        n = len(prompt_ids) - 1
+        if n <= 0:
+            return 0
+        H, nh, hd = self.hidden, self.n_heads, self.head_dim
+        w4 = lambda w: (w.qweight, w.scales, w.qzeros, w.g_idx)
+        x = self.embed[torch.tensor(list(prompt_ids[:n]), device=self.dev)]  # [n, H]
+        pos = torch.arange(n, device=self.dev, dtype=torch.int64)[None, :]
+        for li, ly in enumerate(self.layers):
+            qkv = ops.matmul248(ops.rmsnorm(x, ly['input_norm'], self.model.rms_eps), *w4(ly['qkv']), ly['qkv'].bits, groupsize=ly['qkv'].hint).view(1, n, 3, nh, hd)
+            ops.rotate_half_(qkv[:, :, :2], pos, base=self.model.rope_base)
+            q, k, v = (qkv[0, :, i].transpose(0, 1) for i in range(3))  # [nh, n, hd]
+            self.k_cache[li, 0, :, :n] = k
+            self.v_cache[li, 0, :, :n] = v
+            att = torch.nn.functional.scaled_dot_product_attention(q[None], k[None], v[None], is_causal=True)[0].transpose(0, 1).reshape(n, H)
+            x = x + ops.matmul248(att, *w4(ly['o']), ly['o'].bits, groupsize=ly['o'].hint)
+            h = ops.fused_mlp(ops.rmsnorm(x, ly['post_norm'], self.model.rms_eps), w4(ly['gate']), w4(ly['up']), ly['gate'].bits, ly['gate'].hint)
+            x = x + ops.matmul248(h, *w4(ly['down']), ly['down'].bits, groupsize=ly['down'].hint)
+        return n
+
+    @torch.no_grad()
+    def generate(self, prompt_ids, max_new_tokens, prefill=True):
+        """Greedy decode (batch 1).  One engine, two phases: the prompt is prefilled in one batched pass (tcgen05 GEMM path) into the static KV
+        cache, then the persistent decode kernel takes over token by token; prefill=False feeds the prompt through the decode step instead."""
         assert self.batch == 1
         if len(prompt_ids) < 1 or len(prompt_ids) + max_new_tokens > self.max_seq + 1:
             raise ValueError(f'prompt ({len(prompt_ids)}) + max_new_tokens ({max_new_tokens}) does not fit the KV cache (max_seq = {self.max_seq})')
@@ -287,8 +314,9 @@ class LlamaDecoder:
             raise ValueError(f'prompt token id outside the vocabulary (0..{self.vocab - 1})')
         out = list(prompt_ids)
         self.reset()
+        start = self.prefill(prompt_ids) if (prefill and self.tp is None) else 0
         tok = torch.empty(1, dtype=torch.int32, device=self.dev)
-        for i in range(len(prompt_ids) + max_new_tokens - 1):
+        for i in range(start, len(prompt_ids) + max_new_tokens - 1):
             if i < len(prompt_ids):
                 self.tokens.copy_(torch.tensor([prompt_ids[i]], dtype=torch.int32), non_blocking=False)
             else:
