@@ -35,9 +35,12 @@ def _host_threads():
 
 
 if '--impl' in sys.argv and 'reference' in sys.argv:
-    # the CPU arm uses every host core it may run on; torchrun exports OMP_NUM_THREADS=1, which must not leak into it.
-    # (set before torch / libgomp are loaded)
-    os.environ['OMP_NUM_THREADS'] = os.environ.get('BENCH_CPU_THREADS', str(_host_threads()))
+    # the CPU arm sets its thread count itself (torchrun exports OMP_NUM_THREADS=1, which must not leak into it), before torch / libgomp
+    # are loaded.  32 threads: the restatement is bound by its bit-unpacking loop per 32-column block and two OpenMP runtimes are alive in
+    # the process (torch's and the oracle's); with all 128 hardware threads of the B200 hosts spinning in both, a token took 3.5 - 13.8 s from
+    # run to run, with 8 threads of the build container 4.6 s.  Passive waiting keeps idle workers off the cores.
+    os.environ['OMP_NUM_THREADS'] = os.environ.get('BENCH_CPU_THREADS', str(min(32, _host_threads())))
+    os.environ['OMP_WAIT_POLICY'] = 'passive' 
 
 import torch  # noqa: E402
 
@@ -121,6 +124,7 @@ def cpu_baseline(steps=2, warmup=1):
     ts = c.time_tokens(steps, warmup)
     t = statistics.median(ts)
     threads = int(os.environ.get('OMP_NUM_THREADS', _host_threads()))
+    torch.set_num_threads(min(threads, torch.get_num_threads()) if 'OMP_NUM_THREADS' in os.environ else torch.get_num_threads())
     return {
         'value': 1.0 / t, 'unit': 'tokens/s', 'cores': threads, 'kind': 'port',
         'sample': f'oracle {c.kind} restatement of matmul_248 / fusedmatmul_248 on {threads} host threads: {steps} WHOLE decoded tokens (32 layers x 5 quantized linears at '
@@ -134,8 +138,8 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(int(os.environ['OMP_NUM_THREADS']))
-    steps = min(max(1, args.steps), 12)  # bounded sample: ~3 s per token on 128 threads
-    warm = min(max(0, args.warmup), 2)
+    steps = min(max(1, args.steps), 8)  # bounded sample: a few seconds per token
+    warm = min(max(0, args.warmup), 1)
     base, ts = cpu_baseline(steps, warm)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': 'tokens/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warm,
