@@ -132,7 +132,7 @@ struct MegaParams {
     // H: hidden size (the residual stream, replicated under tensor parallelism); n_heads, Hq = 128 * n_heads, I: this rank's attention heads
     // / attention width / MLP width (the full ones on a single GPU); V: vocabulary, [v0, v1): the lm_head rows of this rank
     int n_layers, H, Hq, I, V, v0, v1, n_heads, max_seq, n_stages, lm_rows;
-    int tp_size, tp_rank;
+    int tp_size, tp_rank, tp_exchange;  // tp_exchange: reduce locally first, then hand slices to the ranks (else: every team REDs into every rank)
     float eps, inv_base, scale;
     const __half* embed;
     const __half* final_norm;
@@ -154,9 +154,12 @@ struct MegaParams {
     float* part;       // [teams][kRec]  attention partial records (m, l, pad, pad, o[128]), one per team and layer
     float* rope_cs;    // [128]: cos[64], sin[64] of this step's position
     unsigned long long* bar;  // [0]: monotonic arrival counter of the grid barrier, [1]: its value when the previous launch ended
-    // tensor parallelism (tp_size > 1): the o_proj / down_proj partial sums of every rank are RED-added into EVERY rank's accumulator over
-    // NVLink (peer pointers), the lm_head slices are stored into every rank's logits, and the three hand-offs that follow them use
-    // a cross-GPU barrier: xbar = this rank's arrival counters, one 256-byte line per source rank, line kMaxTP = value at launch end
+    // tensor parallelism (tp_size > 1): a rank first reduces its o_proj / down_proj partial sums locally (acc_*_loc), then every CTA adds its
+    // slice of that vector into EVERY rank's accumulator over NVLink (peer pointers, red.sys: 4 bytes x H x ranks per hand-off instead of
+    // every team's partials); the lm_head slices are stored into every rank's logits; the hand-offs that follow use a cross-GPU barrier:
+    // xbar = this rank's arrival counters, one 256-byte line per source rank, line kMaxTP = value at launch end
+    float* acc_o_loc;  // [H] this rank's partial sums of o_proj / down_proj before they are handed to the ranks (tp_size > 1)
+    float* acc_d_loc;
     float* acc_o_peer[kMaxTP];
     float* acc_d_peer[kMaxTP];
     __half* logits_peer[kMaxTP];
@@ -427,6 +430,17 @@ __device__ __forceinline__ void tp_barrier(const MegaParams& p, unsigned long lo
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     cta_sync();
+}
+
+// This rank's locally reduced vector (n floats, complete after a grid barrier) is added into every rank's accumulator and cleared for its next use.
+__device__ __forceinline__ void tp_exchange(const MegaParams& p, float* loc, float* const* peers, int n) {
+    const int per = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = blockIdx.x * per, hi = min(n, lo + per);
+    for (int j = lo + threadIdx.x; j < hi; j += kConsumers) {
+        const float v = ld_cg(loc + j);
+        loc[j] = 0.f;
+        for (int q = 0; q < p.tp_size; ++q) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(peers[q] + j), "f"(v) : "memory");
+    }
 }
 
 __device__ __forceinline__ void zero_slice(float* buf, int n) {
@@ -765,7 +779,6 @@ __device__ void stage_range(const MegaParams& p, const TeamCtx& tc, int nk, int 
 
 // One matvec op for this team: consume the stages of its unit range from the ring, RED the results.
 // NM = 2: gate|up as one virtual matrix (out0 = gate accumulators, out1 = up accumulators).
-// peers != nullptr (tensor parallelism, o_proj / down_proj): the result is RED-added into out0's counterpart on every rank.
 template <int NM, int XMODE, bool ACT = false>
 __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& tc, int gs_steps, int K, int N, float* out0, float* out1, const __half* xs_full,
                            const float* xsum_full, const int32_t* perm = nullptr, float* const* peers = nullptr) {
@@ -866,9 +879,9 @@ __device__ void run_matvec(const MegaParams& p, ConsRing& ring, const TeamCtx& t
             gpos += n;
             if (gpos == gs_steps) gpos = 0;
         }
-        if (peers == nullptr || p.tp_size == 1) {
+        if (peers == nullptr) {
             asm volatile("red.global.add.f32 [%0], %1;" ::"l"(outp), "f"(tot) : "memory");  // the warp's 32 columns: one 128-byte line
-        } else {
+        } else {  // tensor parallelism, direct mode: the partial sum goes into out0's counterpart on every rank
             const size_t off = (size_t)(outp - out0);
             for (int q = 0; q < p.tp_size; ++q) asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(peers[q] + off), "f"(tot) : "memory");
         }
@@ -1177,11 +1190,16 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     unsigned long long xgen = 0;  // the same for the cross-GPU barrier (tensor parallelism)
     if (p.tp_size > 1) asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(xgen) : "l"(p.xbar_peer[p.tp_rank] + 32 * kMaxTP) : "memory");
     // after the o_proj, down_proj and lm_head operations every rank needs every rank's contributions
-    auto sync_all_ranks = [&]() {
-        if (p.tp_size > 1)
-            tp_barrier(p, xgen);
-        else
+    auto sync_all_ranks = [&](float* loc, float* const* peers) {
+        if (p.tp_size == 1) {
             grid_barrier(p.bar, gen);
+        } else {
+            if (p.tp_exchange && loc != nullptr) {
+                grid_barrier(p.bar, gen);
+                tp_exchange(p, loc, peers, p.H);
+            }
+            tp_barrier(p, xgen);
+        }
     };
 
     // this step's RoPE angles (quant/fused_attn.py:43,91): freq_i = exp(i * inv_base) * pos
@@ -1228,11 +1246,11 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         zero_slice(p.acc_qkv, 3 * p.Hq);
         {
             OPTRACE_BEGIN(ring);
-            run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.Hq, p.H, p.acc_o, nullptr, xs, xsum, L.o_perm, p.acc_o_peer);
+            run_matvec<1, X_ATTN, ACT>(p, ring, tc, L.o.gs_steps, p.Hq, p.H, p.tp_exchange ? p.acc_o_loc : p.acc_o, nullptr, xs, xsum, L.o_perm, (p.tp_size > 1 && !p.tp_exchange) ? p.acc_o_peer : nullptr);
             OPTRACE_END(ring, l, 2);
         }
         MTRACE(l * 12 + 6);
-        sync_all_ranks();
+        sync_all_ranks(p.acc_o_loc, p.acc_o_peer);
         MTRACE(l * 12 + 7);
         // ---- G ----
         stage_norm<ACT, false>(p, p.resid[cur], p.acc_o, L.post_norm, p.resid[cur ^ 1], xs, xsum, tmp, red_s, L.mlp_perm);
@@ -1250,11 +1268,11 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
         MTRACE(l * 12 + 10);
         {
             OPTRACE_BEGIN(ring);
-            run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.acc_d, nullptr, xs, xsum, nullptr, p.acc_d_peer);
+            run_matvec<1, X_SWIGLU>(p, ring, tc, L.down.gs_steps, p.I, p.H, p.tp_exchange ? p.acc_d_loc : p.acc_d, nullptr, xs, xsum, nullptr, (p.tp_size > 1 && !p.tp_exchange) ? p.acc_d_peer : nullptr);
             OPTRACE_END(ring, l, 4);
         }
         MTRACE(l * 12 + 11);
-        sync_all_ranks();
+        sync_all_ranks(p.acc_d_loc, p.acc_d_peer);
         resid_src = p.resid[cur];
         resid_acc = p.acc_d;
     }
@@ -1263,7 +1281,7 @@ __global__ void __launch_bounds__(kBlock, 1) llama_decode_mega_kernel(const __gr
     zero_slice(p.acc_g, p.I);
     zero_slice(p.acc_u, p.I);
     run_lm_head(p, ring, tc, xs);
-    sync_all_ranks();
+    sync_all_ranks(nullptr, nullptr);
     zero_slice(p.acc_d, p.H);
     if (blockIdx.x == 0) {
         if (tid == 0) {  // every CTA has arrived at the last barrier: the counters rest at these values until the next launch
@@ -1397,7 +1415,7 @@ size_t mega_scratch_bytes(const gptq_llama_model& m, int max_seq) {
     (void)max_seq;
     const size_t max_teams = 1024;  // >= kTeams * SM count of any device this library runs on
     return al256((size_t)m.hidden * 2) * 2 + al256((size_t)3 * m.hidden * 4) + al256((size_t)m.hidden * 4) * 2 + al256((size_t)m.intermediate * 4) * 2 +
-           al256(max_teams * kRec * 4) + al256(128 * 4) + 256 + (kMaxTP + 1) * 256;
+           al256(max_teams * kRec * 4) + al256(128 * 4) + 256 + (kMaxTP + 1) * 256 + al256((size_t)m.hidden * 4) * 2;
 }
 
 cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state& st, uint8_t* scratch, cudaStream_t stream) {
@@ -1450,6 +1468,8 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
     const gptq_llama_tp* tp = st.tp;
     p.tp_size = tp != nullptr ? tp->size : 1;
     p.tp_rank = tp != nullptr ? tp->rank : 0;
+    // measured on 65B: direct peer REDs win up to 4 ranks, the local reduction + slice exchange at 8
+    p.tp_exchange = (tp != nullptr && tp->size > 1) ? (tp->reduce_mode == 0 ? (tp->size > 4) : (tp->reduce_mode == 2)) : 0;
     for (int q = 0; q < p.tp_size; ++q) {
         uint8_t* base = (tp != nullptr && q != tp->rank) ? reinterpret_cast<uint8_t*>(tp->peer_scratch[q]) : scratch;
         p.acc_o_peer[q] = reinterpret_cast<float*>(base + (reinterpret_cast<uint8_t*>(p.acc_o) - scratch));
@@ -1457,6 +1477,8 @@ cudaError_t launch_decode_mega(const gptq_llama_model& m, const gptq_llama_state
         p.xbar_peer[q] = reinterpret_cast<unsigned long long*>(base + (reinterpret_cast<uint8_t*>(xbar) - scratch));
         p.logits_peer[q] = reinterpret_cast<__half*>((tp != nullptr && q != tp->rank) ? tp->peer_logits[q] : st.logits);
     }
+    p.acc_o_loc = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
+    p.acc_d_loc = reinterpret_cast<float*>(take((size_t)m.hidden * 4));
     p.acc_qkv = reinterpret_cast<float*>(take((size_t)3 * p.Hq * 4));
     p.acc_g = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));
     p.acc_u = reinterpret_cast<float*>(take((size_t)m.intermediate * 4));

@@ -50,7 +50,8 @@ MAX_TP = 8
 
 class LlamaTP(ctypes.Structure):
     """struct gptq_llama_tp."""
-    _fields_ = [('size', c_int), ('rank', c_int), ('vocab_begin', c_int), ('vocab_end', c_int), ('peer_scratch', c_void_p * MAX_TP), ('peer_logits', c_void_p * MAX_TP)]
+    _fields_ = [('size', c_int), ('rank', c_int), ('vocab_begin', c_int), ('vocab_end', c_int), ('reduce_mode', c_int), ('peer_scratch', c_void_p * MAX_TP),
+                ('peer_logits', c_void_p * MAX_TP)]
 
 
 class LlamaState(ctypes.Structure):

@@ -122,7 +122,7 @@ class LlamaDecoder:
 
     def __init__(self, layers, embed, final_norm, lm_head, n_heads, rms_eps=1e-6, rope_base=10000.0, batch=1, max_seq=2048, use_graph=True, head_dim=None,
                  tp=None):
-        """tp = (rank, size, vocab_begin, vocab_end): this process holds one tensor-parallel shard (see shard_for_rank / gptq_llama_tp): `layers`,
+        """tp = (rank, size, vocab_begin, vocab_end[, reduce_mode]): this process holds one tensor-parallel shard (see shard_for_rank / gptq_llama_tp): `layers`,
         `lm_head` and `n_heads` are the LOCAL ones, head_dim must be given, and torch.distributed must be initialised (the scratch and logits
         buffers of the ranks are exchanged as CUDA IPC handles)."""
         self.dev = embed.device
@@ -186,7 +186,7 @@ class LlamaDecoder:
     def _setup_tp(self, scratch_bytes):
         """Scratch and logits in IPC-shareable device memory; every rank maps every other rank's buffers (gptq_llama_tp)."""
         import torch.distributed as dist
-        rank, size, v0, v1 = self.tp
+        rank, size, v0, v1 = self.tp[:4]
         assert self.batch == 1 and dist.is_initialized() and dist.get_world_size() == size
 
         def ipc_buffer(nbytes, dtype):
@@ -206,6 +206,7 @@ class LlamaDecoder:
         dist.all_gather_object(handles, (h_scr, h_log))
         t = LlamaTP()
         t.size, t.rank, t.vocab_begin, t.vocab_end = size, rank, v0, v1
+        t.reduce_mode = self.tp[4] if len(self.tp) > 4 else 0
         self._peer_maps = []
         for q, (hs, hl) in enumerate(handles):
             if q == rank:
@@ -377,7 +378,7 @@ def shard_for_rank(layers, lm_head, n_heads, head_dim, rank, size):
     return out, lm_head[v0:v1].contiguous(), hl, (v0, v1)
 
 
-def synthetic_llama_tp(size_name, rank, world, bits=4, groupsize=128, vocab=32000, device='cuda:0', seed=0, n_layers=None, full=None, **kw):
+def synthetic_llama_tp(size_name, rank, world, bits=4, groupsize=128, vocab=32000, device='cuda:0', seed=0, n_layers=None, full=None, reduce_mode=0, **kw):
     """One tensor-parallel rank of the random-init model `synthetic_llama(size_name, seed=seed)` (every rank generates the same full model from the same
     seed layer by layer and keeps its shard), or of the given `full` decoder's weights."""
     hidden, inter, layers, heads = LLAMA_SHAPES[size_name]
@@ -386,7 +387,7 @@ def synthetic_llama_tp(size_name, rank, world, bits=4, groupsize=128, vocab=3200
     hd = hidden // heads
     if full is not None:
         L, lm_head, hl, (v0, v1) = shard_for_rank(full.layers, full.lm_head, heads, hd, rank, world)
-        return LlamaDecoder(L, full.embed, full.final_norm, lm_head, hl, head_dim=hd, tp=(rank, world, v0, v1), **kw)
+        return LlamaDecoder(L, full.embed, full.final_norm, lm_head, hl, head_dim=hd, tp=(rank, world, v0, v1, reduce_mode), **kw)
     gen = torch.Generator(device=dev).manual_seed(seed)
     L = []
     fake_head = torch.empty(0, hidden, device=dev)
@@ -402,7 +403,7 @@ def synthetic_llama_tp(size_name, rank, world, bits=4, groupsize=128, vocab=3200
     lm_head = (torch.randn(vocab, hidden, device=dev, generator=gen) * 0.02).half()
     final_norm = (torch.rand(hidden, device=dev, generator=gen) * 0.2 + 0.9).half()
     v0, v1 = rank * vocab // world, (rank + 1) * vocab // world
-    return LlamaDecoder(L, embed, final_norm, lm_head[v0:v1].contiguous(), heads // world, head_dim=hd, tp=(rank, world, v0, v1), **kw)
+    return LlamaDecoder(L, embed, final_norm, lm_head[v0:v1].contiguous(), heads // world, head_dim=hd, tp=(rank, world, v0, v1, reduce_mode), **kw)
 
 
 def from_hf_quant_model(model, batch=1, max_seq=2048, **kw):

@@ -161,6 +161,7 @@ typedef struct gptq_llama_model {
 typedef struct gptq_llama_tp {
     int size, rank;
     int vocab_begin, vocab_end;
+    int reduce_mode; /* 0: automatic; 1: every team RED-adds its partial sums into every rank; 2: local reduction, then every CTA hands a slice to the ranks */
     void* peer_scratch[GPTQ_MAX_TP];
     void* peer_logits[GPTQ_MAX_TP];
 } gptq_llama_tp;

@@ -71,18 +71,19 @@ def _decode_worker(rank, world, port, q):
             torch.cuda.synchronize()
             ref.append(full.logits[0].float().clone())
         # ... and as `world` tensor-parallel shards: o_proj / down_proj partial sums land in every rank's accumulators over NVLink
-        tp = engine.synthetic_llama_tp('tiny512', rank, world, full=full, max_seq=96)
-        assert tp.launches_per_step() == 1
         worst = 0.0
-        for pos, tok in enumerate(toks):
-            tp.set_input(tok, pos)
-            tp.step()
-            torch.cuda.synchronize()
-            out = tp.logits[0].float()
-            rms = ref[pos].pow(2).mean().sqrt()
-            worst = max(worst, ((out - ref[pos]).abs() / torch.maximum(ref[pos].abs(), rms)).max().item())
-            assert int(tp.next_tokens[0]) == int(out.argmax())
-        dist.barrier()
+        for mode in (1, 2):  # direct peer REDs / local reduction + slice exchange (gptq_llama_tp.reduce_mode)
+            tp = engine.synthetic_llama_tp('tiny512', rank, world, full=full, max_seq=96, reduce_mode=mode)
+            assert tp.launches_per_step() == 1
+            for pos, tok in enumerate(toks):
+                tp.set_input(tok, pos)
+                tp.step()
+                torch.cuda.synchronize()
+                out = tp.logits[0].float()
+                rms = ref[pos].pow(2).mean().sqrt()
+                worst = max(worst, ((out - ref[pos]).abs() / torch.maximum(ref[pos].abs(), rms)).max().item())
+                assert int(tp.next_tokens[0]) == int(out.argmax())
+            dist.barrier()
         q.put((rank, worst))
     finally:
         dist.destroy_process_group()
