@@ -132,6 +132,18 @@ def cpu_baseline(steps=2, warmup=1):
     }, ts
 
 
+def cpu_baseline_subprocess(steps=3, warmup=1):
+    """The cpu_baseline leg of our arm = the reference arm itself on a short sample, in its own process (its thread settings must be in
+    place before torch / libgomp load, and must not disturb the GPU arm)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--steps', str(steps), '--warmup', str(warmup)], capture_output=True,
+                             text=True, timeout=240, env={k: v for k, v in os.environ.items() if k not in ('RANK', 'WORLD_SIZE', 'LOCAL_RANK', 'OMP_NUM_THREADS')})
+        line = [ln for ln in out.stdout.splitlines() if ln.startswith('{')][-1]
+        return json.loads(line)['cpu_baseline']
+    except Exception as e:  # the GPU line must not depend on the host leg
+        return {'value': None, 'unit': 'tokens/s', 'cores': None, 'kind': 'port', 'sample': f'cpu leg failed: {e!r}'}
+
+
 def run_reference(args):
     """`--impl reference`: the reference's own arithmetic on the host cores, rank 0 only."""
     rank = int(os.environ.get('RANK', '0'))
@@ -293,7 +305,7 @@ def run_decode(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_dev, t_e2e = tt.tolist()
     if rank == 0:
-        base, _ = cpu_baseline(2, 1) if (world == 1 and args.config == '7b') else (None, None)
+        base = cpu_baseline_subprocess() if (world == 1 and args.config == '7b') else None
         H, I, V, L = dec.hidden, engine.LLAMA_SHAPES[size][1], dec.vocab, len(dec.layers)
         jobs = 1 if tp else world  # sequences decoded concurrently
         # algorithmic bytes per token: quant linears of the CHECKPOINT (not of derived buffers) + fp16 lm_head + KV cache read at this context
