@@ -103,6 +103,7 @@ class QuantLinear(nn.Module):
         if linear.bias is not None:
             self.bias = linear.bias.detach().clone().half().to(home)
         self._g_key = None
+        self._sorted = None  # derived kernel-form buffers belong to the tensors that were just replaced
 
     # ------------------------------------------------------------------ forward
     def groupsize_hint(self):
