@@ -197,3 +197,40 @@ def test_narrow_bits_are_served_by_the_int4_kernels_through_the_widened_plan(bit
     for M, rel in ((1, 1e-3), (40, 2e-3)):
         x = torch.randn(M, 1024, generator=torch.Generator().manual_seed(M)).half()
         assert_rel_close(ql(x.cuda()), O.qlinear_fwd(x, *cpu, bits), rel=rel, what=f'bits={bits} act={act} M={M}')
+
+
+@pytest.mark.parametrize('bits,gs,act', [(4, 32, False), (4, 64, True), (8, 64, False)])
+def test_solver_to_pack_to_kernel_on_a_bias_block(bits, gs, act):
+    """The whole quantisation-side chain on the GPU for an OPT / GPT-NeoX style block (nn.Linear WITH bias, opt.py:249-285, neox.py:234-273):
+    gptq.quantize_linears (Hessian, Cholesky, blocked updates on the device) -> make_quant_linear -> QuantLinear.pack (GPU packing kernels) ->
+    QuantLinear.forward (CUDA kernels) reproduces the fp16 forward of the on-grid weights the solver left in the layer."""
+    import copy
+    import torch.nn as nn
+    import gptq
+    import quant
+
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = nn.Linear(256, 512, bias=True), nn.Linear(512, 256, bias=True)
+
+        def forward(self, x):
+            return self.fc2(torch.relu(self.fc1(x)))
+
+    torch.manual_seed(bits + gs)
+    blk = Block().cuda()
+    calib = [torch.randn(4, 32, 256, device='cuda') * (torch.rand(256, device='cuda') * 2 + 0.2) for _ in range(2)]
+    res = gptq.quantize_linears(blk, calib, wbits=bits, groupsize=gs, act_order=act)
+    ongrid = copy.deepcopy(blk).half()  # fp16 model carrying the solver's on-grid weights
+    qblk = copy.deepcopy(blk)
+    quant.make_quant_linear(qblk, {n: getattr(qblk, n) for n in res}, bits, gs)
+    for n, (scale, zero, g_idx, _) in res.items():
+        assert isinstance(getattr(qblk, n), quant.QuantLinear) and getattr(qblk, n).bias is not None
+        getattr(qblk, n).pack(getattr(blk, n), scale, zero, g_idx)
+    qblk = qblk.cuda()
+    x = torch.randn(3, 256, device='cuda').half()
+    for n in res:  # layer by layer: the packed layer equals the on-grid fp16 layer (dequantised weights agree to fp16 rounding of the scales)
+        xin = x if n == 'fc1' else torch.relu(ongrid.fc1(x))
+        assert_rel_close(getattr(qblk, n)(xin), getattr(ongrid, n)(xin), rel=4e-3, what=f'{n} bits={bits} gs={gs} act={act}')
+    if act:
+        assert not torch.equal(res['fc1'][2].cpu(), (torch.arange(256) // gs).int())
