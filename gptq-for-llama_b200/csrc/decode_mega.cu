@@ -1,13 +1,13 @@
-// Persistent decode step: ONE cooperative kernel per token (batch 1, int4 kernel-form layers).
+// Persistent decode step: ONE cooperative kernel per token (batch 1, int4 kernel-form layers; optionally one tensor-parallel shard).
 //
 // One CTA per SM (148 on B200), each with two consumer TEAMS of 8 warps and one producer warp per team.
 // Everything a token reads from HBM -- packed weights with their scales/zeros, the KV cache, the fp16 lm_head --
-// is streamed by the producer warps with cp.async.bulk (the TMA unit) into a per-team ring of 17.1 KB stages in
+// is streamed by the producer warps through the TMA unit (cp.async.bulk.tensor / cp.async.bulk) into a per-team ring of 17 KB stages in
 // shared memory, in one fixed order per team for the whole token, so the producers run ahead across operations
 // and across grid barriers: while the consumers synchronise, the next operation's bytes are already landing.
 //
 //   per layer:  Q  qkv matvec      x = rmsnorm(resid [+ fp16(acc_down)])           -> RED acc_qkv
-//               A  attention       q,k,v = fp16(acc_qkv); RoPE; KV append; stream-K over 32-key units -> part
+//               A  attention       q,k,v = fp16(acc_qkv); RoPE; KV append; a head's 32-key units dealt to its teams -> part
 //               O  o_proj matvec   x = combine(part)                                -> RED acc_o
 //               G  gate|up matvec  x = rmsnorm(resid + fp16(acc_o))                 -> RED acc_gate, acc_up
 //               D  down matvec     x = fp16(silu(acc_gate) * acc_up)                -> RED acc_down
@@ -31,6 +31,7 @@
 // Split-K partial sums are accumulated with red.global.add.f32 into fp32 vectors that the NEXT operation
 // rounds to fp16 exactly where the reference rounds (a QuantLinear output is fp16); each vector is re-zeroed
 // one operation after its last reader.  Only the fp32 summation order of those partials is unordered.
+// Tensor parallelism (gptq_llama_tp): the o_proj / down_proj sums also go to the peer GPUs' accumulators (NVLink, see MegaParams).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
