@@ -276,7 +276,7 @@ def run_decode(args):
 
     # ---- the drop-in op in isolation: standalone fused gate/up matvec (gptq_fused_mlp_fwd) over the layers' distinct weights ------
     mlp = None
-    if bits == 4 and not act:
+    if bits == 4 and not act and not tp:
         x = torch.randn(1, dec.hidden, device=dev).half()
         gates = [(ly['gate'], ly['up']) for ly in dec.layers]
 
@@ -337,7 +337,7 @@ def run_decode(args):
                             'frac': step_bytes / t_step / 1e9 / peak / (world if tp else 1), 'peak_source': peak_src + (' per GPU' if tp else ''),
                             'bytes_per_launch': step_bytes, 'us_per_launch': t_step * 1e6, 'frac_of_8TBs': step_bytes / t_step / 8e12,
                             'traffic': NCU_TRAFFIC_BYTES.get(args.config), 'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full, profiles/'}
-        if mlp is None and bits == 4 and not act:
+        if mlp is None and bits == 4 and not act and not tp:
             ach = kbytes / t_k / 1e9
             line['roofline']['standalone_fused_mlp'] = {'kernel': 'qmatvec_int4_kernel<dual> (standalone gptq_fused_mlp_fwd, timed alone over the layers\' distinct weights)',
                                                         'achieved': ach, 'frac': ach / peak, 'bytes_per_launch': kbytes, 'us_per_launch': t_k * 1e6}
