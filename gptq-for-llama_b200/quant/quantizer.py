@@ -38,50 +38,59 @@ class Quantizer(nn.Module):
             return x.reshape(-1, x.shape[-1]).t()
         return x.t()
 
-    def find_params(self, x, weight=False):
-        self.maxq = self.maxq.to(x.device)
-        shape = x.shape
-        rows = self._rows(x, weight)
+    def _range(self, rows):
+        """Per-row [lo, hi] that contains 0; symmetric grids mirror the larger side; all-zero rows get [-1, 1]."""
         lo = rows.amin(1).clamp(max=0)
         hi = rows.amax(1).clamp(min=0)
         if self.sym:
             hi = torch.maximum(lo.abs(), hi)
             lo = torch.where(lo < 0, -hi, lo)
         dead = (lo == 0) & (hi == 0)
-        lo = torch.where(dead, torch.full_like(lo, -1), lo)
-        hi = torch.where(dead, torch.full_like(hi, 1), hi)
+        return torch.where(dead, torch.full_like(lo, -1), lo), torch.where(dead, torch.full_like(hi, 1), hi)
 
-        if self.maxq < 0:
+    def _grid(self, lo, hi, shrink=1.0):
+        """(scale, zero) of the affine grid spanning [shrink * lo, shrink * hi] with maxq + 1 levels."""
+        scale = (shrink * hi - shrink * lo) / self.maxq
+        if self.sym:
+            return scale, torch.full_like(scale, (self.maxq + 1) / 2)
+        return scale, torch.round(-(shrink * lo) / scale)
+
+    def _search_mse(self, rows, lo, hi):
+        """Shrink the range step by step and keep, per row, the grid with the smallest L_norm reconstruction error."""
+        best = torch.full([rows.shape[0]], float('inf'), device=rows.device)
+        for step in range(int(self.maxshrink * self.grid)):
+            s1, z1 = self._grid(lo, hi, 1 - step / self.grid)
+            if self.sym:
+                z1 = self.zero
+            err = (self._quantize(rows, s1.unsqueeze(1), z1.unsqueeze(1), self.maxq) - rows).abs_().pow_(self.norm).sum(1)
+            better = err < best
+            best = torch.where(better, err, best)
+            self.scale = torch.where(better, s1, self.scale)
+            self.zero = torch.where(better, z1, self.zero)
+
+    def find_params(self, x, weight=False):
+        self.maxq = self.maxq.to(x.device)
+        dims = x.shape
+        rows = self._rows(x, weight)
+        lo, hi = self._range(rows)
+        if self.maxq < 0:  # ternary: the two levels are the extremes themselves
             self.scale, self.zero = hi, lo
         else:
-            self.scale = (hi - lo) / self.maxq
-            self.zero = torch.full_like(self.scale, (self.maxq + 1) / 2) if self.sym else torch.round(-lo / self.scale)
-
-        if self.mse:  # shrink the range on a grid, keep the best L_norm error per row
-            best = torch.full([rows.shape[0]], float('inf'), device=x.device)
-            for i in range(int(self.maxshrink * self.grid)):
-                p = 1 - i / self.grid
-                s1 = (p * hi - p * lo) / self.maxq
-                z1 = self.zero if self.sym else torch.round(-(p * lo) / s1)
-                err = (self._quantize(rows, s1.unsqueeze(1), z1.unsqueeze(1), self.maxq) - rows).abs_().pow_(self.norm).sum(1)
-                better = err < best
-                best = torch.where(better, err, best)
-                self.scale = torch.where(better, s1, self.scale)
-                self.zero = torch.where(better, z1, self.zero)
-
-        if not self.perchannel:
-            reps = shape[0] if weight else (shape[1] if len(shape) != 3 else shape[2])
-            self.scale, self.zero = self.scale.repeat(reps), self.zero.repeat(reps)
-
+            self.scale, self.zero = self._grid(lo, hi)
+        if self.mse:
+            self._search_mse(rows, lo, hi)
+        if not self.perchannel:  # one grid for the whole tensor, repeated per output channel
+            if weight:
+                copies = dims[0]
+            else:
+                copies = dims[2] if len(dims) == 3 else dims[1]
+            self.scale, self.zero = self.scale.repeat(copies), self.zero.repeat(copies)
+        # broadcastable against x
         if weight:
-            bshape = [-1] + [1] * (len(shape) - 1)
-        elif len(shape) == 4:
-            bshape = (1, -1, 1, 1)
-        elif len(shape) == 3:
-            bshape = (1, 1, -1)
+            view = [-1] + [1] * (len(dims) - 1)
         else:
-            bshape = (1, -1)
-        self.scale, self.zero = self.scale.reshape(bshape), self.zero.reshape(bshape)
+            view = {4: (1, -1, 1, 1), 3: (1, 1, -1)}.get(len(dims), (1, -1))
+        self.scale, self.zero = self.scale.reshape(view), self.zero.reshape(view)
 
     def quantize(self, x):
         return self._quantize(x, self.scale, self.zero, self.maxq) if self.ready() else x
