@@ -116,3 +116,79 @@ def test_decoder_shards_reassemble():
         seen_heads.append(hc)
         seen_cols.append((c0, c1))
     assert torch.equal(torch.cat(seen_heads), torch.arange(H)) and seen_cols == [(0, 512), (512, 1024)] and seen_vocab == [(0, 48), (48, 96)]
+
+
+def _decode_worker(rank, world, port, q):
+    """One tensor-parallel rank of a decoder step in oracle arithmetic: what the persistent kernel computes per rank (local heads, local MLP
+    slabs, local vocabulary rows), with the two per-layer reductions and the logits gather as gloo collectives."""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        from gptq_b200 import engine
+        H, I, NH, hd, bits, gs, V, T = 512, 1024, 4, 128, 4, 128, 96, 5
+
+        def layer(K, N, seed):
+            qw, s, qz, g, _ = O.random_packed(K, N, bits, gs, seed=seed)
+            return engine.QLayerWeights(qw, (s.float() * 0.2).half(), qz, g, bits, gs)  # smaller scales keep the two-layer activations tame
+
+        gen = torch.Generator().manual_seed(0)
+        layers = [dict(qkv=layer(H, 3 * H, 10 * l + 1), o=layer(H, H, 10 * l + 2), gate=layer(H, I, 10 * l + 3), up=layer(H, I, 10 * l + 4), down=layer(I, H, 10 * l + 5),
+                       input_norm=(torch.rand(H, generator=gen) * 0.2 + 0.9).half(), post_norm=(torch.rand(H, generator=gen) * 0.2 + 0.9).half()) for l in range(2)]
+        lm_head = (torch.randn(V, H, generator=gen) * 0.05).half()
+        fnorm = torch.ones(H).half()
+        x0 = (torch.randn(1, H, generator=gen) * 0.5).half()
+        kc = (torch.randn(2, NH, T, hd, generator=gen) * 0.5).half()  # cached rows [0, T) per layer
+        vc = (torch.randn(2, NH, T, hd, generator=gen) * 0.5).half()
+        w4 = lambda w: (w.qweight, w.scales, w.qzeros, w.g_idx)
+
+        def step(lys, head, heads, reduce_):
+            """heads: the global head indices this caller owns; reduce_: sums a partial [1, H] over the ranks (identity for the full model)."""
+            x = x0.clone()
+            nh = len(heads)
+            for li, ly in enumerate(lys):
+                qkv = O.qlinear_fwd(O.rmsnorm_fwd(x, ly['input_norm'], 1e-6), *w4(ly['qkv']), bits).view(1, 1, 3, nh, hd).clone()
+                O.rope_inplace(qkv[:, :, :2], torch.tensor([[T]]))
+                qh, kh, vh = qkv[0, 0, 0], qkv[0, 0, 1], qkv[0, 0, 2]
+                K = torch.cat([kc[li, heads], kh[:, None, :]], 1).float()
+                Vv = torch.cat([vc[li, heads], vh[:, None, :]], 1).float()
+                att = torch.einsum('ht,htd->hd', torch.softmax(torch.einsum('hd,htd->ht', qh.float(), K) * hd**-0.5, -1), Vv).half().reshape(1, nh * hd)
+                x = x + reduce_(O.qlinear_fwd(att, *w4(ly['o']), bits).float()).half()
+                hmid = O.fused_mlp_fwd(O.rmsnorm_fwd(x, ly['post_norm'], 1e-6), w4(ly['gate']), w4(ly['up']), bits)
+                x = x + reduce_(O.qlinear_fwd(hmid, *w4(ly['down']), bits).float()).half()
+            return (O.rmsnorm_fwd(x, fnorm, 1e-6).float() @ head.float().t())[0]
+
+        full_logits = step(layers, lm_head, list(range(NH)), lambda t: t)
+        shard, head_local, hl, (v0, v1) = engine.shard_for_rank(layers, lm_head, NH, hd, rank, world)
+
+        def allreduce(t):
+            t = t.clone()
+            dist.all_reduce(t)
+            return t
+
+        local = step(shard, head_local, list(range(rank * hl, (rank + 1) * hl)), allreduce)
+        gathered = [torch.empty(V // world) for _ in range(world)]
+        dist.all_gather(gathered, local.contiguous())
+        logits = torch.cat(gathered)
+        rms = full_logits.pow(2).mean().sqrt()
+        err = ((logits - full_logits).abs() / torch.maximum(full_logits.abs(), rms)).max().item()
+        q.put((rank, err, (v0, v1)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp_decoder_step_world2_gloo():
+    """The tensor-parallel decode path's host logic on CPU (gloo, world 2): sharding by heads / MLP slabs / vocabulary rows + one reduction after
+    o_proj and after down_proj reproduces the unsharded decoder step (oracle arithmetic on both sides; the GPU version, where the reductions are
+    peer-memory REDs inside the persistent kernel, is tests/test_gpu_tp.py)."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29650 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_decode_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=5) for _ in range(2))
+    assert [r[2] for r in res] == [(0, 48), (48, 96)]
+    assert max(r[1] for r in res) < 5e-3, res  # fp16 rounding of the per-rank partial outputs before the sum
