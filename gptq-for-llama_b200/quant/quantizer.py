@@ -52,7 +52,7 @@ class Quantizer(nn.Module):
         """(scale, zero) of the affine grid spanning [shrink * lo, shrink * hi] with maxq + 1 levels."""
         scale = (shrink * hi - shrink * lo) / self.maxq
         if self.sym:
-            return scale, torch.full_like(scale, (self.maxq + 1) / 2)
+            return scale, torch.full_like(scale, (int(self.maxq) + 1) / 2)
         return scale, torch.round(-(shrink * lo) / scale)
 
     def _search_mse(self, rows, lo, hi):
